@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by executing the reference's OWN, UNMODIFIED Python files from
+/root/reference (TEST INFRASTRUCTURE; runs only in the build container, where /root/reference
+exists -- the committed .npz files are what travels).
+
+MLX 0.7.0 cannot be installed here, so `mlx.core` / `mlx.nn` / `mlx.optimizers` resolve to the
+NumPy-backed stand-in in oracle/mlx_shim (see its docstring for the assumed MLX semantics).
+`sample_from_inverse_cdf_torch` is pure torch and runs for real.
+
+    python oracle/make_golden.py            # rewrites tests/golden/*.npz
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("NMX_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def main():
+    sys.path.insert(0, os.path.join(HERE, "mlx_shim"))
+    sys.path.insert(0, REF)
+    import mlx.core as mx
+    import mlx.nn as mnn
+    from mlx_nerf import sampling
+    from mlx_nerf.sampling import uniform, linear_disparity
+    from mlx_nerf.models import NeRF as RN, embedding
+    from mlx_nerf.encoding.sinusoidal import SinusoidalEncoding
+    from mlx_nerf.rendering import render, ray
+    from mlx_nerf.ops import pose
+
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # ---- sampling: sample_z (uniform.py:7-18, linear_disparity.py:8-19)
+    near = rng.uniform(0.5, 3.0, size=(7, 1)).astype(np.float32)
+    far = (near + rng.uniform(1.0, 5.0, size=(7, 1))).astype(np.float32)
+    g = {"near": near, "far": far}
+    for n in (2, 64, 192):
+        g[f"uniform_{n}"] = uniform.sample_z(near, far, n)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g[f"lindisp_{n}"] = linear_disparity.sample_z(near, far, n)
+    np.savez_compressed(os.path.join(OUT, "sample_z.npz"), **g)
+
+    # ---- sample_from_inverse_cdf_torch (sampling/__init__.py:101-178), real torch
+    g = {}
+    for tag, B, n, N in (("a", 33, 64, 128), ("b", 5, 16, 40), ("c", 9, 64, 128)):
+        z = np.sort(rng.uniform(2.0, 6.0, size=(B, n)).astype(np.float32), axis=-1)
+        if tag == "c":  # peaky weights, incl. exact zeros and a one-hot row
+            w = (rng.random(size=(B, n, 1)) ** 8).astype(np.float32)
+            w[0] = 0.0
+            w[1] = 0.0
+            w[1, 17] = 1.0
+        else:
+            w = rng.random(size=(B, n, 1)).astype(np.float32)
+        torch.manual_seed(1234 + B)
+        u = torch.rand([B, N])  # same draw the function makes first thing from the global RNG
+        torch.manual_seed(1234 + B)
+        out = sampling.sample_from_inverse_cdf_torch(torch.from_numpy(z), torch.from_numpy(w), N)
+        # the CDF the reference built (re-derived with the same torch ops, :113-131)
+        wt = torch.from_numpy(w)[..., 0] + 0.01
+        ws = torch.sum(wt, dim=-1, keepdim=True)
+        pdf = wt / ws
+        cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, axis=-1))
+        cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+        inds = torch.searchsorted(cdf, u, side="right")
+        g.update({f"{tag}_z": z, f"{tag}_w": w, f"{tag}_u": u.numpy(), f"{tag}_out": out.numpy(),
+                  f"{tag}_cdf": cdf.numpy(), f"{tag}_inds": inds.numpy()})
+    np.savez_compressed(os.path.join(OUT, "sample_pdf.npz"), **g)
+
+    # ---- PE flavour A (models/embedding.py) and embed()
+    pos = rng.uniform(-4.0, 4.0, size=(6, 5, 3)).astype(np.float32)
+    dirs = rng.standard_normal(size=(6, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    e_pos, d_pos = embedding.get_embedder(10)
+    e_dir, d_dir = embedding.get_embedder(4)
+    e_2d, d_2d = embedding.get_embedder(6, n_input_dims=2)
+    xy = rng.uniform(-1, 1, size=(11, 2)).astype(np.float32)
+    np.savez_compressed(
+        os.path.join(OUT, "pe_embedder.npz"), pos=pos, dirs=dirs,
+        pe_pos=e_pos(pos.reshape(-1, 3)), pe_dir=e_dir(dirs), d_pos=d_pos, d_dir=d_dir,
+        embed=embedding.embed(pos, e_pos, dirs, e_dir), xy=xy, pe_xy=e_2d(xy), d_2d=d_2d)
+
+    # ---- PE flavour B (encoding/sinusoidal.py), integer pixel coords as the image demo feeds
+    X = np.stack(np.meshgrid(np.arange(0, 256, 37), np.arange(0, 256, 41), indexing="ij"), -1).reshape(-1, 2)
+    se = SinusoidalEncoding(2, 10, min_freq_exp=0.0, max_freq_exp=8.0, is_include_input=False)
+    se3 = SinusoidalEncoding(3, 4, is_include_input=True)
+    x3 = rng.uniform(-2, 2, size=(9, 3)).astype(np.float32)
+    # MLX promotes int32 * float32 -> float32 (NumPy would go to float64), so the integer coordinates
+    # are pre-cast to float32 before entering the reference code under the NumPy stand-in.
+    np.savez_compressed(os.path.join(OUT, "pe_sinusoidal.npz"), X=X.astype(np.int32), enc=se(X.astype(np.float32)),
+                        out_dim=se.get_out_dim(), x3=x3, enc3=se3(x3), out_dim3=se3.get_out_dim())
+
+    # ---- NeRF.forward (models/NeRF.py:160-243): view-dir net, no-view net, image net (small widths)
+    def dump_params(model, prefix, g):
+        for i, l in enumerate(model.list_linears_pos):
+            g[f"{prefix}list_linears_pos.{i}.weight"] = l.weight
+            g[f"{prefix}list_linears_pos.{i}.bias"] = l.bias
+        for name in ("feature_linear", "alpha_linear", "rgb_linear", "output_linear"):
+            if hasattr(model, name):
+                g[f"{prefix}{name}.weight"] = getattr(model, name).weight
+                g[f"{prefix}{name}.bias"] = getattr(model, name).bias
+        if hasattr(model, "list_linears_dir"):
+            g[f"{prefix}list_linears_dir.0.weight"] = model.list_linears_dir[0].weight
+            g[f"{prefix}list_linears_dir.0.bias"] = model.list_linears_dir[0].bias
+
+    mnn.seed(7)
+    g = {}
+    net_v = RN.NeRF(n_layers=8, width_layers=64, channel_input=63, channel_input_views=27, channel_output=5,
+                    list_skip_connection_layers=[4], is_use_view_directions=True)
+    net_n = RN.NeRF(n_layers=8, width_layers=64, channel_input=63, channel_input_views=27, channel_output=5,
+                    list_skip_connection_layers=[4], is_use_view_directions=False)
+    net_i = RN.NeRF(n_layers=8, width_layers=32, channel_input=40, channel_input_views=0, channel_output=3,
+                    is_use_view_directions=False)
+    xin = rng.standard_normal(size=(19, 90)).astype(np.float32)
+    xim = rng.standard_normal(size=(13, 40)).astype(np.float32)
+    dump_params(net_v, "v/", g)
+    dump_params(net_n, "n/", g)
+    dump_params(net_i, "i/", g)
+    g.update(x=xin, y_v=net_v.forward(xin), y_n=net_n.forward(xin[:, :63]), x_img=xim, y_i=net_i.forward(xim))
+    np.savez_compressed(os.path.join(OUT, "nerf_forward.npz"), **g)
+
+    # ---- raw2outputs (rendering/render.py:20-96)
+    g = {}
+    for tag, B, n in (("a", 17, 64), ("b", 4, 192), ("c", 3, 5)):
+        raw = rng.standard_normal(size=(B, n, 4)).astype(np.float32)
+        raw[..., 3] *= 3.0  # negative and positive densities (T can exceed 1: reference quirk)
+        z = np.sort(rng.uniform(2.0, 6.0, size=(B, n)).astype(np.float32), axis=-1)
+        d = rng.standard_normal(size=(B, 3)).astype(np.float32)
+        for wb in (False, True):
+            outs = render.raw2outputs(raw, z, d, 0, wb)
+            for name, o in zip(("rgb", "disp", "acc", "weights", "depth"), outs):
+                g[f"{tag}_{int(wb)}_{name}"] = o
+        g.update({f"{tag}_raw": raw, f"{tag}_z": z, f"{tag}_d": d})
+    np.savez_compressed(os.path.join(OUT, "raw2outputs.npz"), **g)
+
+    # ---- render_rays / render_rays_eval end to end (render.py:112-241) with the small view-dir net
+    B, n, N = 12, 64, 128
+    o = rng.uniform(-1, 1, size=(B, 3)).astype(np.float32) + np.array([0, 0, 4], np.float32)
+    d = rng.standard_normal(size=(B, 3)).astype(np.float32)
+    vd = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    rays = np.concatenate([o, d, 2.0 * np.ones((B, 1), np.float32), 6.0 * np.ones((B, 1), np.float32), vd], -1).astype(np.float32)
+    qf = lambda inputs, viewdirs, model: RN.run_model(inputs, e_pos, viewdirs, e_dir, model, netchunk=256)
+    mnn.seed(11)
+    net_f = RN.NeRF(n_layers=8, width_layers=64, channel_input=63, channel_input_views=27, channel_output=5,
+                    list_skip_connection_layers=[4], is_use_view_directions=True)
+    g = {"rays": rays}
+    dump_params(net_v, "c/", g)
+    dump_params(net_f, "f/", g)
+    r1 = render.render_rays(rays, net_v, qf, n, retraw=True, white_bkgd=True)
+    for k, v in r1.items():
+        g[f"rr_{k}"] = v
+    torch.manual_seed(99)
+    u = torch.rand([B, N]).numpy()
+    torch.manual_seed(99)
+    r2 = render.render_rays_eval(rays, net_v, qf, n, white_bkgd=True, N_importance=N, network_fine=net_f)
+    for k, v in r2.items():
+        g[f"re_{k}"] = v
+    g["u"] = u
+    np.savez_compressed(os.path.join(OUT, "render_rays.npz"), **g)
+
+    # ---- get_rays / pose_spherical (rendering/ray.py:7-35, ops/pose.py:7-58)
+    H, W, focal = 6, 8, 9.5
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = np.asarray(pose.pose_spherical(30.0, -30.0, 4.0))
+    ro, rd = ray.get_rays(H, W, K, c2w[:3, :4])
+    np.savez_compressed(os.path.join(OUT, "rays.npz"), K=K, c2w=c2w, rays_o=np.array(ro), rays_d=np.array(rd), H=H, W=W)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+"""Pins the oracle (CPU restatement) against golden vectors produced by the reference's own
+unmodified code (oracle/make_golden.py).  CPU-only."""
+import numpy as np
+import torch
+
+from oracle import sampling as osamp, encoding as oenc, models as omodels, rendering as orend
+
+
+def test_sample_z(golden):
+    g = golden("sample_z")
+    for n in (2, 64, 192):
+        np.testing.assert_array_equal(osamp.sample_z_uniform(g["near"], g["far"], n), g[f"uniform_{n}"])
+        np.testing.assert_array_equal(osamp.sample_z_lindisp(g["near"], g["far"], n), g[f"lindisp_{n}"])
+
+
+def test_sample_pdf_indices_bit_exact_given_cdf(golden):
+    g = golden("sample_pdf")
+    for tag in "abc":
+        out, inds = osamp.sample_pdf(g[f"{tag}_z"], g[f"{tag}_w"], g[f"{tag}_u"], cdf=g[f"{tag}_cdf"], return_inds=True)
+        np.testing.assert_array_equal(inds, g[f"{tag}_inds"])
+        np.testing.assert_array_equal(out, g[f"{tag}_out"])  # same CDF -> identical fp32 result
+
+
+def test_sample_pdf_own_cdf(golden):
+    """CDF built by the oracle (fp64 sum/prefix) vs torch's (ISA-dependent fp32 sum): <= few ulp,
+    and the end-to-end sample mismatch rate stays tiny."""
+    g = golden("sample_pdf")
+    for tag in "abc":
+        cdf = osamp.build_cdf(g[f"{tag}_w"])
+        np.testing.assert_allclose(cdf, g[f"{tag}_cdf"], rtol=0, atol=4e-7)
+        out, inds = osamp.sample_pdf(g[f"{tag}_z"], g[f"{tag}_w"], g[f"{tag}_u"], return_inds=True)
+        mism = np.mean(inds != g[f"{tag}_inds"])
+        assert mism < 2e-3, mism
+        ok = inds == g[f"{tag}_inds"]
+        np.testing.assert_allclose(out[ok], g[f"{tag}_out"][ok], rtol=1e-5, atol=1e-5)
+
+
+def test_pe_embedder(golden):
+    g = golden("pe_embedder")
+    assert oenc.embedder_out_dim(10) == int(g["d_pos"]) == 63
+    assert oenc.embedder_out_dim(4) == int(g["d_dir"]) == 27
+    assert oenc.embedder_out_dim(6, 2) == int(g["d_2d"]) == 24
+    np.testing.assert_array_equal(oenc.embedder_embed(g["pos"].reshape(-1, 3), 10), g["pe_pos"])
+    np.testing.assert_array_equal(oenc.embedder_embed(g["dirs"], 4), g["pe_dir"])
+    np.testing.assert_array_equal(oenc.embed(g["pos"], 10, g["dirs"], 4), g["embed"])
+    np.testing.assert_array_equal(oenc.embedder_embed(g["xy"], 6, 2), g["pe_xy"])
+    # the reference's frequency quirk: squares, with a dead band 0
+    np.testing.assert_array_equal(oenc.embedder_freq_bands(10), np.arange(10, dtype=np.float32) ** 2)
+
+
+def test_pe_sinusoidal(golden):
+    g = golden("pe_sinusoidal")
+    assert oenc.sinusoidal_out_dim(2, 10) == int(g["out_dim"]) == 40
+    np.testing.assert_array_equal(oenc.sinusoidal_encode(g["X"], 10, 0.0, 8.0), g["enc"])
+    assert oenc.sinusoidal_out_dim(3, 4, True) == int(g["out_dim3"])
+    np.testing.assert_array_equal(oenc.sinusoidal_encode(g["x3"], 4, None, None, True), g["enc3"])
+
+
+def _load_net(g, prefix, **kw):
+    net = omodels.NeRF(**kw)
+    for k in list(net.params.keys()):
+        arr = g[prefix + k]
+        assert tuple(arr.shape) == tuple(net.params[k].shape), (k, arr.shape, net.params[k].shape)
+        net.params[k] = torch.from_numpy(arr.copy())
+    return net
+
+
+def test_nerf_forward(golden):
+    g = golden("nerf_forward")
+    v = _load_net(g, "v/", n_layers=8, width_layers=64, channel_input=63, channel_input_views=27,
+                  channel_output=5, is_use_view_directions=True)
+    n = _load_net(g, "n/", n_layers=8, width_layers=64, channel_input=63, channel_input_views=27,
+                  channel_output=5, is_use_view_directions=False)
+    i = _load_net(g, "i/", n_layers=8, width_layers=32, channel_input=40, channel_input_views=0,
+                  channel_output=3, is_use_view_directions=False)
+    x = torch.from_numpy(g["x"])
+    np.testing.assert_allclose(v.forward(x).numpy(), g["y_v"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(n.forward(x[:, :63]).numpy(), g["y_n"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(i.forward(torch.from_numpy(g["x_img"])).numpy(), g["y_i"], rtol=2e-5, atol=2e-6)
+
+
+def test_raw2outputs(golden):
+    g = golden("raw2outputs")
+    for tag in "abc":
+        for wb in (0, 1):
+            outs = orend.raw2outputs(g[f"{tag}_raw"], g[f"{tag}_z"], g[f"{tag}_d"], 0, bool(wb))
+            for name, o in zip(("rgb", "disp", "acc", "weights", "depth"), outs):
+                ref = g[f"{tag}_{wb}_{name}"]
+                assert tuple(o.shape) == tuple(ref.shape), name
+                np.testing.assert_allclose(o.numpy(), ref, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(ref).max()), err_msg=name)
+
+
+def test_render_rays_and_eval(golden):
+    g = golden("render_rays")
+    kw = dict(n_layers=8, width_layers=64, channel_input=63, channel_input_views=27, channel_output=5,
+              is_use_view_directions=True)
+    c = _load_net(g, "c/", **kw)
+    f = _load_net(g, "f/", **kw)
+    qf = orend.make_query_fn(10, 4, netchunk=256)
+    r1 = orend.render_rays(g["rays"], c, qf, 64, retraw=True, white_bkgd=True)
+    for k in ("rgb_map", "disp_map", "acc_map", "z_vals", "weights", "raw"):
+        ref = g[f"rr_{k}"]
+        np.testing.assert_allclose(r1[k].numpy(), ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(ref).max()), err_msg=k)
+    r2 = orend.render_rays_eval(g["rays"], c, qf, 64, white_bkgd=True, N_importance=128, network_fine=f,
+                                u_vals=g["u"])
+    for k in ("rgb_map", "disp_map", "acc_map", "rgb_coarse", "z_vals", "weights"):
+        ref = g[f"re_{k}"]
+        np.testing.assert_allclose(r2[k].numpy(), ref, rtol=2e-3, atol=2e-4 * max(1.0, np.abs(ref).max()), err_msg=k)
+
+
+def test_get_rays_pose(golden):
+    g = golden("rays")
+    c2w = orend.pose_spherical(30.0, -30.0, 4.0)
+    np.testing.assert_allclose(c2w, g["c2w"], rtol=0, atol=1e-7)
+    ro, rd = orend.get_rays(int(g["H"]), int(g["W"]), g["K"], g["c2w"][:3, :4])
+    np.testing.assert_array_equal(np.array(ro), g["rays_o"])
+    np.testing.assert_array_equal(rd, g["rays_d"])
+
+
+def test_hash_known_answers():
+    """Canonical uint32 wrap semantics, hand-computed."""
+    T = 19
+    c = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [3, 5, 7], [-1, 2, 3]], dtype=np.int32)
+    exp = []
+    for x, y, z in c.tolist():
+        h = ((x & 0xFFFFFFFF) * 1) & 0xFFFFFFFF
+        h ^= ((y & 0xFFFFFFFF) * 2654435761) & 0xFFFFFFFF
+        h ^= ((z & 0xFFFFFFFF) * 805459861) & 0xFFFFFFFF
+        exp.append(h & ((1 << T) - 1))
+    np.testing.assert_array_equal(oenc.hashgrid_hash(c, T), np.array(exp))
+    res = oenc.hashgrid_scaled_res(16, 16, 2048)
+    assert res[0] == 16 and res.shape == (16,) and res[-1] in (2047.0, 2048.0)
