@@ -1,0 +1,156 @@
+/*
+ * nmx.h -- C ABI of libnmx.so, the B200 (sm_100a) implementation of the volume-learning hot path of
+ * piljoong-jeong/nerf_meets_mlx.
+ *
+ * The reference has no FFI: its boundary is the Python call surface of mlx_nerf/{sampling,encoding,
+ * models,rendering}.  Each entry point below names the reference function (file:line, relative to the
+ * reference repo root) whose arithmetic it replaces; the Python package `nerf_meets_mlx_b200` mirrors
+ * those functions' names/signatures and calls these symbols through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (borrowed for the duration of the stream-ordered call) unless
+ *     the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value 0 = success, non-zero = cudaError_t or NMX_E_* (message via nmx_last_error_string);
+ *   - no hidden global state except a per-process cache of kernel attributes / driver entry points;
+ *   - all tensors are dense row-major; fp32 unless stated; 16-byte aligned base pointers.
+ */
+#ifndef NMX_H_
+#define NMX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMX_VERSION 100
+#define NMX_E_BADARG 10001
+#define NMX_E_UNSUPPORTED 10002
+#define NMX_E_DRIVER 10003
+
+int nmx_version(void);
+const char* nmx_last_error_string(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t nmx_launch_count(void);
+
+/* ---------------------------------------------------------------- sampling (K1) */
+/* uniform.sample_z (sampling/uniform.py:7-18) / linear_disparity.sample_z (linear_disparity.py:8-19).
+ * near, far: [B]; z: [B, n].  t_i = fp32(i) * fp32(1/(n-1)); z = near*(1-t) + far*t (two-product form). */
+int nmx_sample_z_fwd(const float* near, const float* far, float* z, int64_t B, int n, int lindisp, void* stream);
+/* add_noise_z (sampling/__init__.py:10-31) with the uniform draw t_rand [B, n] explicit. */
+int nmx_add_noise_z_fwd(const float* z, const float* t_rand, float* z_out, int64_t B, int n, float strength, void* stream);
+/* pos = o + z*d (rendering/render.py:142): rays [B, ray_stride] (o at col 0, d at col 3), z [B, n] -> pos [B, n, 3] */
+int nmx_ray_points_fwd(const float* rays, int ray_stride, const float* z, float* pos, int64_t B, int n, void* stream);
+
+/* ---------------------------------------------------------------- positional encodings (K2a/K2b) */
+/* Embedder.embed (models/embedding.py:35-71): [x, sin(f0 x), cos(f0 x), ...], f_k = k^2 (reference quirk).
+ * x: [P, in_dim] -> out: [P, (include_input?in_dim:0) + 2*in_dim*n_freqs] */
+int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n_freqs, int include_input, void* stream);
+/* SinusoidalEncoding.__call__ (encoding/sinusoidal.py:39-66): sin([s, s + fp32(pi/2)]), s = x[:,d]*bands[k]
+ * (dim-major, freq-minor); optional input appended at the end.  bands: [n_freqs] fp32 on device. */
+int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim, int n_freqs,
+                          int include_input, void* stream);
+
+/* ---------------------------------------------------------------- multires hash grid (K2c) */
+/* MultiHashEncoding.hash (encoding/multi_hash.py:61-77): coords [M, 3] int32 -> idx [M] int32,
+ * (x*1 ^ y*2654435761 ^ z*805459861) mod 2^log2_T in uint32 wraparound arithmetic. */
+int nmx_hashgrid_hash(const int32_t* coords, int32_t* idx, int64_t M, int log2_T, void* stream);
+/* MultiHashEncoding.__call__ (encoding/multi_hash.py:79-137): x [P,3], tables [L, 2^log2_T, F], scaled_res [L]
+ * -> out [P, L*F]; optional idx_out [P, L, 8] int32 (corner table indices, reference corner order). F in {1,2,4}. */
+int nmx_hashgrid_fwd(const float* x, const float* tables, const float* scaled_res, float* out, int32_t* idx_out,
+                     int64_t P, int L, int F, int log2_T, void* stream);
+/* gradient w.r.t. tables: d_tables [L, T, F] += scatter(d_out [P, L*F]) (caller zeroes d_tables). */
+int nmx_hashgrid_bwd(const float* x, const float* scaled_res, const float* d_out, float* d_tables,
+                     int64_t P, int L, int F, int log2_T, void* stream);
+
+/* ---------------------------------------------------------------- compositing (K4) */
+/* raw2outputs (rendering/render.py:20-96).  raw [B,n,4] (rgb, sigma), z [B,n], rays_d [B, d_stride] (first 3 used),
+ * optional noise [B,n] (N(0,1)) scaled by raw_noise_std.  Outputs: rgb [B,3], disp [B], acc [B], weights [B,n],
+ * depth [B].  Any output pointer may be NULL. */
+int nmx_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                      float raw_noise_std, int white_bkgd, float* rgb, float* disp, float* acc, float* weights,
+                      float* depth, int64_t B, int n, void* stream);
+/* backward of raw2outputs w.r.t. raw.  d_rgb [B,3] required; d_disp/d_acc/d_depth [B], d_weights [B,n] optional (NULL).
+ * d_raw [B,n,4].  n <= 256. */
+int nmx_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, const float* noise,
+                      float raw_noise_std, int white_bkgd, const float* d_rgb, const float* d_disp,
+                      const float* d_acc, const float* d_depth, const float* d_weights, float* d_raw,
+                      int64_t B, int n, void* stream);
+
+/* ---------------------------------------------------------------- inverse-CDF resampling (K5) */
+/* sample_from_inverse_cdf_torch (sampling/__init__.py:101-178) + sort-merge (rendering/render.py:225).
+ * z [B,n], weights [B,n], u [B,N].  cdf_in [B,n+1] optional (NULL -> built in-kernel: fp64 sum / prefix).
+ * Outputs (each optional): z_imp [B,N] unsorted (the reference function's result), inds [B,N] int32
+ * (searchsorted-right), cdf_out [B,n+1], z_merged [B,n+N] ascending. */
+int nmx_sample_pdf_fwd(const float* z, const float* weights, const float* u, const float* cdf_in, float eps,
+                       float* z_imp, int32_t* inds, float* cdf_out, float* z_merged,
+                       int64_t B, int n, int N, void* stream);
+/* stand-alone sort(concat(a [B,na], b [B,nb])) -> out [B, na+nb]; a need not be sorted. */
+int nmx_sort_merge_z(const float* a, const float* b, float* out, int64_t B, int na, int nb, void* stream);
+
+/* ---------------------------------------------------------------- loss / optimiser (K6) */
+/* mean((pred - target)^2) over count elements (__test_nerf.py:88,124); loss [1] is accumulated (caller zeroes);
+ * d_pred = 2 (pred - target) / count * grad_scale (NULL to skip). */
+int nmx_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* d_pred, int64_t count,
+                    float grad_scale, void* stream);
+/* optim.Adam of MLX 0.7.0 (NeRF.py:120), no bias correction: m=b1 m+(1-b1)g; v=b2 v+(1-b2)g^2;
+ * p -= lr*m/(sqrt(v)+eps).  With bias_correction!=0 uses the standard corrected form at step t. */
+int nmx_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2,
+                  float eps, int bias_correction, int64_t t, void* stream);
+
+/* ---------------------------------------------------------------- NeRF MLP (K3), tcgen05/TMEM/TMA */
+/* Opaque plan for one NeRF network (models/NeRF.py:160-243) in its reference geometry.
+ * Packed parameter layout (fp32, `params`, count = nmx_mlp_param_count): for each Linear in the order
+ *   list_linears_pos[0..D-1], then (view-dir head) feature_linear, alpha_linear, list_linears_dir[0], rgb_linear
+ *   or (no-view head) output_linear:  weight [out, in] row-major followed by bias [out]. */
+typedef struct nmx_mlp_plan nmx_mlp_plan;
+
+typedef struct {
+  int n_layers;       /* D (8) */
+  int width;          /* W (256); must be a multiple of 64, <= 256 */
+  int in_pos;         /* encoded position channels (63 for Embedder N=10, 40 for image PE) */
+  int in_dir;         /* encoded view-dir channels (27) or 0 */
+  int out_ch;         /* no-view head output channels (channel_output) */
+  int skip_layer;     /* index i such that [input_pos, h] is concatenated after layer i; -1 = none */
+  int use_viewdirs;   /* 1 = view-dir head (rgb,alpha), 0 = output_linear */
+  int enc_kind;       /* how the kernel generates inputs: 0 = rows of a precomputed fp32 [P, in_pos+in_dir] tensor,
+                         1 = Embedder PE fused in the operand producer from rays/z (n_freqs_pos / n_freqs_dir),
+                         2 = SinusoidalEncoding fused from x [P, in_dim] and bands */
+  int n_freqs_pos, n_freqs_dir;
+} nmx_mlp_config;
+
+int64_t nmx_mlp_param_count(const nmx_mlp_config* cfg);
+int nmx_mlp_plan_create(const nmx_mlp_config* cfg, int64_t max_points, nmx_mlp_plan** out);
+void nmx_mlp_plan_destroy(nmx_mlp_plan* plan);
+/* bytes of device workspace the plan needs for `max_points` with/without saved activations */
+int64_t nmx_mlp_workspace_bytes(const nmx_mlp_plan* plan, int training);
+/* refresh the bf16 operand copies of the weights from fp32 params (call after every optimiser step) */
+int nmx_mlp_load_params(nmx_mlp_plan* plan, const float* params, void* workspace, void* stream);
+
+/* NeRF.forward via run_model (models/NeRF.py:25-48,201-243).
+ *   enc_kind 0: x [P, in_pos+in_dir] fp32 (already encoded).
+ *   enc_kind 1: rays [B, ray_stride] (o, d, near, far, viewdirs at the last 3 cols), z [B, n]; P = B*n.
+ *   enc_kind 2: x [P, in_dim] raw coordinates, bands [n_freqs_pos].
+ * out [P, out_cols] fp32 (out_cols = 4 for the view-dir head, out_ch otherwise).
+ * save_activations != 0 keeps what nmx_mlp_bwd needs in the workspace. */
+int nmx_mlp_fwd(nmx_mlp_plan* plan, void* workspace, const float* x_or_rays, int ray_stride, const float* z,
+                const float* bands, float* out, int64_t B, int n, int save_activations, void* stream);
+/* gradients of all parameters (packed like `params`, fp32, overwritten) from d_out [P, out_cols]. */
+int nmx_mlp_bwd(nmx_mlp_plan* plan, void* workspace, const float* x_or_rays, int ray_stride, const float* z,
+                const float* bands, const float* d_out, float* d_params, int64_t B, int n, void* stream);
+
+/* generic bf16 GEMM building block on tcgen05 (exposed for unit tests / profiling):
+ * D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]);  A,B bf16 row-major (K-major), D bf16 or fp32. */
+int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, void* D, int64_t M, int N, int K,
+                  int relu, int d_is_fp32, void* stream);
+/* dW[M,N] (fp32, accumulated: caller zeroes) += dY[P,M]^T * X[P,N]; bf16 row-major inputs, read as MN-major
+ * UMMA operands (no transposes); M % 128 == 0, N % 64 == 0, N <= 256. */
+int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, int64_t P, int M, int N, void* stream);
+/* out[N] (fp32, accumulated) += column sums of Y[P,N] bf16 (bias gradients). */
+int nmx_colsum_bf16(const void* Y, float* out, int64_t P, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMX_H_ */

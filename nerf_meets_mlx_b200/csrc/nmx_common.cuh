@@ -1,0 +1,87 @@
+// Shared helpers for libnmx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nmx.h"
+
+namespace nmx {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define NMX_CHECK_ARG(cond, msg)                              \
+  do {                                                        \
+    if (!(cond)) {                                            \
+      ::nmx::set_error("%s: bad argument: %s", __func__, msg); \
+      return NMX_E_BADARG;                                    \
+    }                                                         \
+  } while (0)
+
+#define NMX_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::nmx::set_error("%s: %s failed: %s", __func__, #expr, cudaGetErrorString(_e));      \
+      return (int)_e;                                                                     \
+    }                                                                                     \
+  } while (0)
+
+#define NMX_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ::nmx::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(_e));  \
+      return (int)_e;                                                                     \
+    }                                                                                     \
+    ::nmx::count_launch();                                                                \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// inclusive prefix sum across the warp (lane order)
+__device__ __forceinline__ float warp_scan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// inclusive suffix sum across the warp (lane i gets sum over lanes >= i)
+__device__ __forceinline__ float warp_rscan_incl(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ double warp_scan_incl_f64(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)kNumSMs * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace nmx

@@ -1,0 +1,191 @@
+// libnmx core: error state, launch counter, sampling (K1) and stand-alone positional encodings (K2a/K2b).
+#include <stdarg.h>
+#include <atomic>
+
+#include "nmx_common.cuh"
+
+namespace nmx {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace nmx
+
+using namespace nmx;
+
+extern "C" int nmx_version(void) { return NMX_VERSION; }
+extern "C" const char* nmx_last_error_string(void) { return nmx::g_err; }
+extern "C" int64_t nmx_launch_count(void) { return nmx::g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// K1: depth sampling.  Explicit _rn intrinsics pin the reference's operation order (no FMA contraction):
+//   t = i*step (+0);  z = near*(1-t) + far*t             (sampling/uniform.py:13-16)
+//   z = 1/(1/(near*(1-t)) + 1/(far*t))                   (sampling/linear_disparity.py:14-17, as written)
+__global__ void sample_z_kernel(const float* __restrict__ near, const float* __restrict__ far,
+                                float* __restrict__ z, int64_t total, int n, float step, int lindisp) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = idx / n;
+    int i = (int)(idx - b * n);
+    float t = __fmul_rn((float)i, step);
+    float nr = near[b], fr = far[b];
+    float a = __fmul_rn(nr, __fsub_rn(1.0f, t));
+    float c = __fmul_rn(fr, t);
+    float v;
+    if (!lindisp) {
+      v = __fadd_rn(a, c);
+    } else {
+      v = __fdiv_rn(1.0f, __fadd_rn(__fdiv_rn(1.0f, a), __fdiv_rn(1.0f, c)));
+    }
+    z[idx] = v;
+  }
+}
+
+extern "C" int nmx_sample_z_fwd(const float* near, const float* far, float* z, int64_t B, int n, int lindisp,
+                                void* stream) {
+  NMX_CHECK_ARG(B >= 0 && n >= 2, "B >= 0, n >= 2");
+  if (B == 0) return 0;
+  float step = (float)((1.0 - 0.0) / (double)(n - 1));
+  int64_t total = B * n;
+  sample_z_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, z, total, n, step, lindisp);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// add_noise_z (sampling/__init__.py:17-29): mids, upper=[mids, z_last], lower=[z_0, mids];
+// z = lower + (upper-lower) * (t_rand*strength)
+__global__ void add_noise_z_kernel(const float* __restrict__ z, const float* __restrict__ t_rand,
+                                   float* __restrict__ out, int64_t total, int n, float strength) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(idx % n);
+    float zi = z[idx];
+    float upper = (i == n - 1) ? zi : __fmul_rn(0.5f, __fadd_rn(zi, z[idx + 1]));
+    float lower = (i == 0) ? zi : __fmul_rn(0.5f, __fadd_rn(z[idx - 1], zi));
+    float t = __fmul_rn(t_rand[idx], strength);
+    out[idx] = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
+  }
+}
+
+extern "C" int nmx_add_noise_z_fwd(const float* z, const float* t_rand, float* z_out, int64_t B, int n,
+                                   float strength, void* stream) {
+  NMX_CHECK_ARG(B >= 0 && n >= 1, "B >= 0, n >= 1");
+  if (B == 0) return 0;
+  int64_t total = B * n;
+  if (strength <= 0.0f) {  // sampling/__init__.py:14-15 returns the input unchanged
+    if (z_out != z) NMX_CUDA(cudaMemcpyAsync(z_out, z, total * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+  }
+  add_noise_z_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(z, t_rand, z_out, total, n, strength);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// pos = o + z*d (rendering/render.py:142)
+__global__ void ray_points_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
+                                  float* __restrict__ pos, int64_t total, int n) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pt = idx / 3;
+    int c = (int)(idx - pt * 3);
+    int64_t b = pt / n;
+    const float* r = rays + b * ray_stride;
+    pos[idx] = __fadd_rn(r[c], __fmul_rn(z[pt], r[3 + c]));
+  }
+}
+
+extern "C" int nmx_ray_points_fwd(const float* rays, int ray_stride, const float* z, float* pos, int64_t B, int n,
+                                  void* stream) {
+  NMX_CHECK_ARG(B >= 0 && n >= 1 && ray_stride >= 6, "B >= 0, n >= 1, ray_stride >= 6");
+  if (B == 0) return 0;
+  int64_t total = B * n * 3;
+  ray_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rays, ray_stride, z, pos, total, n);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: Embedder PE (models/embedding.py:35-71).  Channel c of the output:
+//   c < inc           -> x[c]                      (inc = include_input ? in_dim : 0)
+//   else k=(c-inc)/(2*in_dim), r=(c-inc)%(2*in_dim), fn = r/in_dim (0 sin, 1 cos), d = r%in_dim,
+//        f_k = k^2 (reference quirk) ; out = fn(x[d]*f_k)
+// Full-range sinf/cosf (no fast-math): arguments reach |x|*81.
+__global__ void pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t total, int in_dim,
+                                   int n_freqs, int inc) {
+  int out_dim = inc + 2 * in_dim * n_freqs;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = idx / out_dim;
+    int c = (int)(idx - p * out_dim);
+    float v;
+    if (c < inc) {
+      v = x[p * in_dim + c];
+    } else {
+      int q = c - inc;
+      int k = q / (2 * in_dim);
+      int r = q - k * 2 * in_dim;
+      int fn = r / in_dim;
+      int d = r - fn * in_dim;
+      float f = (float)(k * k);
+      float a = __fmul_rn(x[p * in_dim + d], f);
+      v = fn ? cosf(a) : sinf(a);
+    }
+    out[idx] = v;
+  }
+}
+
+extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n_freqs, int include_input,
+                                   void* stream) {
+  NMX_CHECK_ARG(P >= 0 && in_dim >= 1 && n_freqs >= 0, "P >= 0, in_dim >= 1, n_freqs >= 0");
+  if (P == 0) return 0;
+  int inc = include_input ? in_dim : 0;
+  int64_t total = P * (inc + 2 * in_dim * n_freqs);
+  if (total == 0) return 0;
+  pe_embedder_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, total, in_dim, n_freqs, inc);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// K2b: SinusoidalEncoding (encoding/sinusoidal.py:49-66).  out[c]:
+//   c < in_dim*n_freqs      -> sin(x[d]*band[k]),            d = c / n_freqs, k = c % n_freqs
+//   c < 2*in_dim*n_freqs    -> sin(x[d]*band[k] + fp32(pi/2))  (the reference's cos)
+//   else                    -> x[c - 2*in_dim*n_freqs]
+__global__ void pe_sinusoidal_kernel(const float* __restrict__ x, const float* __restrict__ bands,
+                                     float* __restrict__ out, int64_t total, int in_dim, int n_freqs, int out_dim) {
+  const float half_pi = 1.57079637050628662109375f;  // fp32(pi/2)
+  int half = in_dim * n_freqs;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = idx / out_dim;
+    int c = (int)(idx - p * out_dim);
+    float v;
+    if (c < 2 * half) {
+      int q = (c < half) ? c : c - half;
+      int d = q / n_freqs;
+      int k = q - d * n_freqs;
+      float s = __fmul_rn(x[p * in_dim + d], bands[k]);
+      if (c >= half) s = __fadd_rn(s, half_pi);
+      v = sinf(s);
+    } else {
+      v = x[p * in_dim + (c - 2 * half)];
+    }
+    out[idx] = v;
+  }
+}
+
+extern "C" int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim,
+                                     int n_freqs, int include_input, void* stream) {
+  NMX_CHECK_ARG(P >= 0 && in_dim >= 1 && n_freqs >= 1, "P >= 0, in_dim >= 1, n_freqs >= 1");
+  if (P == 0) return 0;
+  int out_dim = 2 * in_dim * n_freqs + (include_input ? in_dim : 0);
+  int64_t total = P * out_dim;
+  pe_sinusoidal_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, bands, out, total, in_dim, n_freqs, out_dim);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,527 @@
+// K3 building blocks: bf16 GEMMs on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands staged
+// by TMA into 128B-swizzled shared memory), warp-specialised and persistent.
+//
+//   gemm_kmajor_kernel : D[M,N] = epi(A[M,K] * B[N,K]^T)      -- layer forward and dgrad (B = W or W^T copy)
+//       A may be the K-concatenation of two row-major bf16 tensors (skip connection / view-dir concat).
+//       epi: +bias, (+ row_vec (x) col_vec), ReLU or ReLU-mask from a saved activation, -> bf16 (or fp32).
+//   wgrad_kernel       : dW[M,N] += dY[P,M]^T * X[P,N]        -- contraction over points, MN-major operands read
+//       straight from the row-major activations (no transposes), split over points, fp32 vector-atomic reduce.
+//
+// Tile: 128 points (UMMA M=128, cta_group::1) x N<=256 (full layer width, so activations are read once) x K=64 per
+// stage.  Warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quadrant
+// = warp_id % 4).  TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <mutex>
+
+#include "nmx_common.cuh"
+#include "nmx_sm100.cuh"
+
+using namespace nmx;
+using namespace nmx::sm100;
+
+namespace nmx {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return NMX_E_DRIVER;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p rows=%llu cols=%llu ld=%llu box=[%u,%u]", (int)r, base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+    return NMX_E_DRIVER;
+  }
+  return 0;
+}
+
+}  // namespace nmx
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+struct GemmArgs {
+  int a0_col, a0_k, a1_col, a1_k;  // K segments of A (elements; multiples of 64); a1_k may be 0
+  int b_col;                       // first K column of B to use
+  int M, N;
+  const float* bias;      // [N] or null
+  void* D;                // bf16 or fp32 [M, ldd]
+  int ldd;
+  int out_fp32;
+  int relu;
+  const __nv_bfloat16* mask;  // saved post-ReLU activation [M, ldmask]; output *= (mask > 0)
+  int ldmask;
+  const float* row_vec;   // optional rank-1 term row_vec[m*row_stride] * col_vec[n] added before the mask
+  int row_stride;
+  const float* col_vec;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTileBytes = STAGES * kStageBytes;
+  static constexpr int kBarOff = kTileBytes;                    // full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
+  static constexpr int kBiasOff = kTmemPtrOff + 16;             // bias[BN] + colvec[BN]
+  static constexpr int kTotal = kBiasOff + 2 * BN * 4;
+  static constexpr int kAlloc = kTotal + 1024;                  // slack for manual 1024 B alignment
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
+  float* s_colv = s_bias + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = args.N;
+  const int num_tiles = (args.M + BM - 1) / BM;
+  const int num_kb = (args.a0_k + args.a1_k) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarp0) tmem_alloc<512>(tmem_ptr);
+  for (int i = threadIdx.x; i < BN; i += kThreads) {
+    s_bias[i] = (args.bias != nullptr && i < N) ? args.bias[i] : 0.0f;
+    s_colv[i] = (args.col_vec != nullptr && i < N) ? args.col_vec[i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = L::kABytes + (uint32_t)N * BK * 2;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::kStageBytes;
+          uint8_t* sB = sA + L::kABytes;
+          mbar_arrive_expect_tx(&full[stage], tx);
+          int k = kb * BK;
+          if (k < args.a0_k) tma_load_2d(sA, &tmA0, &full[stage], args.a0_col + k, tile * BM);
+          else tma_load_2d(sA, &tmA1, &full[stage], args.a1_col + (k - args.a0_k), tile * BM);
+          tma_load_2d(sB, &tmB, &full[stage], args.b_col + k, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    // ================================ epilogue warps ================================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = tile * BM + q * 32 + lane;
+      const bool row_ok = row < args.M;
+      const float rv = (args.row_vec != nullptr && row_ok) ? args.row_vec[(size_t)row * args.row_stride] : 0.0f;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + as * BN + c0 + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j] + rv * s_colv[c0 + j];
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (args.mask != nullptr && row_ok) {
+          const uint4* mp = reinterpret_cast<const uint4*>(args.mask + (size_t)row * args.ldmask + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 m = __ldg(mp + g);
+            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (!(__bfloat162float(mb[j]) > 0.0f)) v[g * 8 + j] = 0.0f;
+          }
+        }
+        if (row_ok) {
+          if (args.out_fp32) {
+            float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.D) + (size_t)row * args.ldd + c0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) dp[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.D) + (size_t)row * args.ldd + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              dp[g] = make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
+                                 pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarp0) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradArgs {
+  int dy_col, x_col;  // first column of dY / X to use
+  int P;              // points (contraction length)
+  int M, N;           // M = 128 per CTA m-tile (grid.y tiles), N multiple of 64, <= 256
+  float* dW;          // fp32 [M_total, ldw], accumulated with atomics at column offset w_col
+  int ldw, w_col;
+  int kb_per_cta;     // 64-point blocks per CTA
+};
+
+template <int STAGES>
+struct WgradSmem {
+  static constexpr int kABytes = 2 * 64 * 64 * 2;   // two 64(M) x 64(P) boxes
+  static constexpr int kBBytes = 4 * 64 * 64 * 2;   // up to four 64(N) x 64(P) boxes
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 1) * 8;
+  static constexpr int kTotal = kTmemPtrOff + 16;
+  static constexpr int kAlloc = kTotal + 1024;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs args) {
+  using L = WgradSmem<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = args.N;
+  const int nb = N / 64;
+  const int m_tile = blockIdx.y;
+  const int total_kb = (args.P + 63) / 64;
+  const int kb0 = blockIdx.x * args.kb_per_cta;
+  const int kb1 = min(total_kb, kb0 + args.kb_per_cta);
+  const int num_kb = max(kb1 - kb0, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarp0) tmem_alloc<256>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (num_kb == 0) {  // nothing to contribute (uniform across the CTA)
+    __syncthreads();
+    if (warp == kEpiWarp0) tmem_dealloc<256>(tmem_base);
+    return;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = L::kABytes + (uint32_t)nb * 64 * 64 * 2;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * L::kStageBytes;
+        uint8_t* sB = sA + L::kABytes;
+        mbar_arrive_expect_tx(&full[stage], tx);
+        const int p = kb * 64;
+        tma_load_2d(sA, &tmDY, &full[stage], args.dy_col + m_tile * 128, p);
+        tma_load_2d(sA + 8192, &tmDY, &full[stage], args.dy_col + m_tile * 128 + 64, p);
+        for (int j = 0; j < nb; ++j) tma_load_2d(sB + j * 8192, &tmX, &full[stage], args.x_col + j * 64, p);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes;
+        // MN-major SW128: LBO = 8192 B between 64-wide M/N atoms (separate TMA boxes), SBO = 1024 B per 8 points
+        const uint64_t adesc = make_smem_desc(a_addr, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(b_addr, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 points = 16 rows of 128 B = 2048 B -> +128 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int m = m_tile * 128 + q * 32 + lane;
+    float* wrow = args.dW + (size_t)m * args.ldw + args.w_col;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(q * 32) << 16), r);
+      tmem_ld_wait();
+      if (m < args.M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarp0) tmem_dealloc<256>(tmem_base);
+}
+
+// column sums of a bf16 matrix (bias gradients): out[n] += sum_p Y[p, col0 + n]
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, int ld, int col0, int N, int64_t P, float* __restrict__ out) {
+  // block: 256 threads = 8 row-groups x 32 column-pair lanes; each lane owns 2 adjacent columns per 64-col chunk
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  __shared__ float s[8][64];
+  for (int c0 = 0; c0 < N; c0 += 64) {
+    float a0 = 0.f, a1 = 0.f;
+    int c = c0 + lane * 2;
+    if (c < N) {
+      for (int64_t p = (int64_t)blockIdx.x * 8 + rg; p < P; p += (int64_t)gridDim.x * 8) {
+        __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(Y + p * ld + col0 + c);
+        a0 += __bfloat162float(v.x);
+        a1 += __bfloat162float(v.y);
+      }
+    }
+    s[rg][lane * 2] = a0;
+    s[rg][lane * 2 + 1] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64 && c0 + threadIdx.x < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) t += s[g][threadIdx.x];
+      atomicAdd(out + c0 + threadIdx.x, t);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+namespace nmx {
+
+// Host-side launchers (internal C++ API used by nmx_mlp.cu and the C ABI test hook).
+struct GemmDesc {
+  const void* A0; int64_t a0_rows; int a0_cols, a0_ld, a0_col, a0_k;
+  const void* A1; int a1_cols, a1_ld, a1_col, a1_k;   // A1 may be null
+  const void* B; int b_rows, b_cols, b_ld, b_col;     // B: [N, K] row-major bf16
+  int64_t M; int N;
+  const float* bias; void* D; int ldd; int out_fp32; int relu;
+  const void* mask; int ldmask;
+  const float* row_vec; int row_stride; const float* col_vec;
+};
+
+int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0) return 0;
+  if (g.N % 32 != 0 || g.N < 32 || g.N > 256) { set_error("gemm: N must be a multiple of 32 in [32,256] (got %d)", g.N); return NMX_E_BADARG; }
+  if (g.a0_k % 64 || g.a1_k % 64 || g.a0_k <= 0) { set_error("gemm: K segments must be positive multiples of 64"); return NMX_E_BADARG; }
+  if (g.M > 0x7fffffff - 256) { set_error("gemm: M too large"); return NMX_E_BADARG; }
+  CUtensorMap tA0, tA1, tB;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tA0, g.A0, g.a0_rows, g.a0_cols, g.a0_ld, BM))) return rc;
+  if (g.A1 != nullptr && g.a1_k > 0) {
+    if ((rc = make_tmap_bf16_2d(&tA1, g.A1, g.a0_rows, g.a1_cols, g.a1_ld, BM))) return rc;
+  } else {
+    tA1 = tA0;
+  }
+  if ((rc = make_tmap_bf16_2d(&tB, g.B, g.b_rows, g.b_cols, g.b_ld, (uint32_t)g.N))) return rc;
+  GemmArgs a;
+  a.a0_col = g.a0_col; a.a0_k = g.a0_k; a.a1_col = g.a1_col; a.a1_k = (g.A1 ? g.a1_k : 0);
+  a.b_col = g.b_col; a.M = (int)g.M; a.N = g.N; a.bias = g.bias; a.D = g.D; a.ldd = g.ldd; a.out_fp32 = g.out_fp32;
+  a.relu = g.relu; a.mask = (const __nv_bfloat16*)g.mask; a.ldmask = g.ldmask; a.row_vec = g.row_vec;
+  a.row_stride = g.row_stride; a.col_vec = g.col_vec;
+  int tiles = (int)((g.M + BM - 1) / BM);
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (g.N > 128) {
+    using L = GemmSmem<256, 4>;
+    static bool attr = false;
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    gemm_kmajor_kernel<256, 4><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, a);
+  } else {
+    using L = GemmSmem<128, 6>;
+    static bool attr = false;
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    gemm_kmajor_kernel<128, 6><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, a);
+  }
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+struct WgradDesc {
+  const void* dY; int dy_cols, dy_ld, dy_col;   // [P, dy_cols] bf16
+  const void* X; int x_cols, x_ld, x_col;       // [P, x_cols] bf16
+  int64_t P; int M, N;                          // M multiple of 128, N multiple of 64 (<= 256)
+  float* dW; int ldw, w_col;
+};
+
+int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
+  if (g.P <= 0) return 0;
+  if (g.M % 128 || g.N % 64 || g.N > 256 || g.N <= 0) { set_error("wgrad: M %% 128, N %% 64, N <= 256 required (M=%d N=%d)", g.M, g.N); return NMX_E_BADARG; }
+  CUtensorMap tDY, tX;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tDY, g.dY, g.P, g.dy_cols, g.dy_ld, 64))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tX, g.X, g.P, g.x_cols, g.x_ld, 64))) return rc;
+  WgradArgs a;
+  a.dy_col = g.dy_col; a.x_col = g.x_col; a.P = (int)g.P; a.M = g.M; a.N = g.N; a.dW = g.dW; a.ldw = g.ldw; a.w_col = g.w_col;
+  int m_tiles = g.M / 128;
+  int total_kb = (int)((g.P + 63) / 64);
+  int splits = kNumSMs / m_tiles;
+  if (splits > total_kb) splits = total_kb;
+  a.kb_per_cta = (total_kb + splits - 1) / splits;
+  splits = (total_kb + a.kb_per_cta - 1) / a.kb_per_cta;
+  using L = WgradSmem<4>;
+  static bool attr = false;
+  if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+  wgrad_kernel<4><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, a);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out, cudaStream_t stream) {
+  if (P <= 0 || N <= 0) return 0;
+  int64_t blocks = (P + 63) / 64;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  colsum_bf16_kernel<<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)Y, ld, col0, N, P, out);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace nmx
+
+// C ABI test hooks -----------------------------------------------------------------------------------------------
+extern "C" int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, void* D, int64_t M, int N, int K,
+                             int relu, int d_is_fp32, void* stream) {
+  NMX_CHECK_ARG(A && Bm && D && M >= 0 && K > 0, "A, B, D non-null; M >= 0; K > 0");
+  nmx::GemmDesc g{};
+  g.A0 = A; g.a0_rows = M; g.a0_cols = K; g.a0_ld = K; g.a0_col = 0; g.a0_k = K;
+  g.A1 = nullptr; g.a1_k = 0;
+  g.B = Bm; g.b_rows = N; g.b_cols = K; g.b_ld = K; g.b_col = 0;
+  g.M = M; g.N = N; g.bias = bias; g.D = D; g.ldd = N; g.out_fp32 = d_is_fp32; g.relu = relu;
+  return nmx::launch_gemm(g, (cudaStream_t)stream);
+}
+
+extern "C" int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, int64_t P, int M, int N, void* stream) {
+  NMX_CHECK_ARG(dY && X && dW && P >= 0, "dY, X, dW non-null; P >= 0");
+  nmx::WgradDesc g{};
+  g.dY = dY; g.dy_cols = M; g.dy_ld = M; g.dy_col = 0;
+  g.X = X; g.x_cols = N; g.x_ld = N; g.x_col = 0;
+  g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = N; g.w_col = 0;
+  return nmx::launch_wgrad(g, (cudaStream_t)stream);
+}
+
+extern "C" int nmx_colsum_bf16(const void* Y, float* out, int64_t P, int N, void* stream) {
+  NMX_CHECK_ARG(Y && out && P >= 0 && N % 2 == 0, "Y, out non-null; N even");
+  return nmx::launch_colsum(Y, N, 0, N, P, out, (cudaStream_t)stream);
+}

@@ -1,0 +1,69 @@
+// K6: MSE loss (+ its gradient) and the Adam update of the reference's training step
+// (entrypoints/__test_nerf.py:88,124,128-145; models/NeRF.py:120).  Pure streaming kernels, float4 vectorised.
+#include "nmx_common.cuh"
+
+using namespace nmx;
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
+           float* __restrict__ d_pred, int64_t count, float inv_count, float grad_scale) {
+  float acc = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float d = pred[i] - target[i];
+    acc += d * d;
+    if (d_pred != nullptr) d_pred[i] = 2.0f * d * inv_count * grad_scale;
+  }
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    float v = (lane < (int)(blockDim.x >> 5)) ? s[lane] : 0.0f;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(loss, v * inv_count);
+  }
+}
+
+// MLX-0.7 Adam (no bias correction) or the standard bias-corrected form.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t count, float lr, float b1, float b2, float eps, float c1, float c2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+  }
+}
+
+}  // namespace
+
+extern "C" int nmx_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* d_pred, int64_t count,
+                               float grad_scale, void* stream) {
+  NMX_CHECK_ARG(count >= 1 && pred && target && loss, "count >= 1; pred, target, loss non-null");
+  int blocks = grid_for(count, 256, 2);
+  mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, loss, d_pred, count, 1.0f / (float)count, grad_scale);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int nmx_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1,
+                             float b2, float eps, int bias_correction, int64_t t, void* stream) {
+  NMX_CHECK_ARG(count >= 0 && p && g && m && v, "count >= 0; p, g, m, v non-null");
+  if (count == 0) return 0;
+  float c1 = 1.0f, c2 = 1.0f;
+  if (bias_correction) {
+    c1 = 1.0f / (1.0f - powf(b1, (float)t));
+    c2 = 1.0f / (1.0f - powf(b2, (float)t));
+  }
+  adam_kernel<<<grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, b1, b2, eps, c1, c2);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}

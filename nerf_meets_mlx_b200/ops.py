@@ -1,0 +1,201 @@
+"""Tensor-level wrappers over the C ABI (include/nmx.h): allocate outputs, pass raw device pointers and the
+current CUDA stream.  No CPU path exists; every function raises if the extension is missing or inputs are not
+contiguous CUDA tensors."""
+import torch
+
+from ._lib_loader import call, f32, i32, i64, ptr, require_cuda, stream
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------- sampling
+def sample_z(near, far, n_samples, lindisp=False):
+    near, far = _f32c(near).reshape(-1), _f32c(far).reshape(-1)
+    require_cuda(near, far)
+    B = near.numel()
+    z = torch.empty((B, n_samples), dtype=torch.float32, device=near.device)
+    call("nmx_sample_z_fwd", ptr(near), ptr(far), ptr(z), i64(B), i32(n_samples), i32(1 if lindisp else 0), stream())
+    return z
+
+
+def add_noise_z(z_vals, t_rand, strength):
+    z = _f32c(z_vals)
+    require_cuda(z)
+    n = z.shape[-1]
+    B = z.numel() // n
+    t = _f32c(t_rand)
+    out = torch.empty_like(z)
+    call("nmx_add_noise_z_fwd", ptr(z), ptr(t), ptr(out), i64(B), i32(n), f32(strength), stream())
+    return out
+
+
+def ray_points(rays, z):
+    rays, z = _f32c(rays), _f32c(z)
+    require_cuda(rays, z)
+    B, n = z.shape
+    pos = torch.empty((B, n, 3), dtype=torch.float32, device=z.device)
+    call("nmx_ray_points_fwd", ptr(rays), i32(rays.shape[1]), ptr(z), ptr(pos), i64(B), i32(n), stream())
+    return pos
+
+
+# ----------------------------------------------------------------------------------------- encodings
+def pe_embedder(x, n_freqs, include_input=True):
+    x = _f32c(x)
+    require_cuda(x)
+    in_dim = x.shape[-1]
+    P = x.numel() // in_dim
+    out_dim = (in_dim if include_input else 0) + 2 * in_dim * n_freqs
+    out = torch.empty((P, out_dim), dtype=torch.float32, device=x.device)
+    call("nmx_pe_embedder_fwd", ptr(x), ptr(out), i64(P), i32(in_dim), i32(n_freqs), i32(1 if include_input else 0), stream())
+    return out.reshape(*x.shape[:-1], out_dim)
+
+
+def pe_sinusoidal(x, bands, include_input=False):
+    x, bands = _f32c(x), _f32c(bands)
+    require_cuda(x, bands)
+    in_dim = x.shape[-1]
+    P = x.numel() // in_dim
+    nf = bands.numel()
+    out_dim = 2 * in_dim * nf + (in_dim if include_input else 0)
+    out = torch.empty((P, out_dim), dtype=torch.float32, device=x.device)
+    call("nmx_pe_sinusoidal_fwd", ptr(x), ptr(bands), ptr(out), i64(P), i32(in_dim), i32(nf), i32(1 if include_input else 0), stream())
+    return out
+
+
+def hashgrid_hash(coords, log2_T):
+    c = coords.to(torch.int32).contiguous()
+    require_cuda(c)
+    M = c.numel() // 3
+    idx = torch.empty(c.shape[:-1], dtype=torch.int32, device=c.device)
+    call("nmx_hashgrid_hash", ptr(c), ptr(idx), i64(M), i32(log2_T), stream())
+    return idx
+
+
+def hashgrid_fwd(x, tables, scaled_res, log2_T, return_idx=False):
+    x, tables, scaled_res = _f32c(x), _f32c(tables), _f32c(scaled_res)
+    require_cuda(x, tables, scaled_res)
+    P = x.shape[0]
+    L, T, F = tables.shape
+    assert T == 1 << log2_T
+    out = torch.empty((P, L * F), dtype=torch.float32, device=x.device)
+    idx = torch.empty((P, L, 8), dtype=torch.int32, device=x.device) if return_idx else None
+    call("nmx_hashgrid_fwd", ptr(x), ptr(tables), ptr(scaled_res), ptr(out), ptr(idx), i64(P), i32(L), i32(F), i32(log2_T), stream())
+    return (out, idx) if return_idx else out
+
+
+def hashgrid_bwd(x, scaled_res, d_out, L, F, log2_T):
+    x, scaled_res, d_out = _f32c(x), _f32c(scaled_res), _f32c(d_out)
+    require_cuda(x, scaled_res, d_out)
+    P = x.shape[0]
+    d_tables = torch.zeros((L, 1 << log2_T, F), dtype=torch.float32, device=x.device)
+    call("nmx_hashgrid_bwd", ptr(x), ptr(scaled_res), ptr(d_out), ptr(d_tables), i64(P), i32(L), i32(F), i32(log2_T), stream())
+    return d_tables
+
+
+# ----------------------------------------------------------------------------------------- compositing
+def composite_fwd(raw, z, rays_d, noise=None, raw_noise_std=0.0, white_bkgd=False):
+    raw, z, rays_d = _f32c(raw), _f32c(z), _f32c(rays_d)
+    require_cuda(raw, z, rays_d)
+    B, n = z.shape
+    assert raw.shape == (B, n, 4), f"raw must be [B, n, 4], got {tuple(raw.shape)}"
+    dev = z.device
+    rgb = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    disp = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    acc = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    weights = torch.empty((B, n, 1), dtype=torch.float32, device=dev)
+    depth = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    nz = _f32c(noise) if (noise is not None and raw_noise_std > 0) else None
+    call("nmx_composite_fwd", ptr(raw), ptr(z), ptr(rays_d), i32(rays_d.shape[-1]), ptr(nz), f32(raw_noise_std),
+         i32(1 if white_bkgd else 0), ptr(rgb), ptr(disp), ptr(acc), ptr(weights), ptr(depth), i64(B), i32(n), stream())
+    return rgb, disp, acc, weights, depth
+
+
+def composite_bwd(raw, z, rays_d, d_rgb, d_disp=None, d_acc=None, d_depth=None, d_weights=None, noise=None,
+                  raw_noise_std=0.0, white_bkgd=False):
+    raw, z, rays_d, d_rgb = _f32c(raw), _f32c(z), _f32c(rays_d), _f32c(d_rgb)
+    require_cuda(raw, z, rays_d, d_rgb)
+    B, n = z.shape
+    opt = [None if t is None else _f32c(t) for t in (d_disp, d_acc, d_depth, d_weights)]
+    nz = _f32c(noise) if (noise is not None and raw_noise_std > 0) else None
+    d_raw = torch.empty((B, n, 4), dtype=torch.float32, device=z.device)
+    call("nmx_composite_bwd", ptr(raw), ptr(z), ptr(rays_d), i32(rays_d.shape[-1]), ptr(nz), f32(raw_noise_std),
+         i32(1 if white_bkgd else 0), ptr(d_rgb), ptr(opt[0]), ptr(opt[1]), ptr(opt[2]), ptr(opt[3]), ptr(d_raw),
+         i64(B), i32(n), stream())
+    return d_raw
+
+
+# ----------------------------------------------------------------------------------------- resampling
+def sample_pdf(z, weights, u, eps=1e-5, cdf=None, want_inds=False, want_cdf=False, want_merged=True, want_imp=True):
+    z, u = _f32c(z), _f32c(u)
+    require_cuda(z, u)
+    B, n = z.shape
+    N = u.shape[-1]
+    w = None if weights is None else _f32c(weights).reshape(B, n)
+    c_in = None if cdf is None else _f32c(cdf)
+    dev = z.device
+    z_imp = torch.empty((B, N), dtype=torch.float32, device=dev) if want_imp else None
+    inds = torch.empty((B, N), dtype=torch.int32, device=dev) if want_inds else None
+    cdf_out = torch.empty((B, n + 1), dtype=torch.float32, device=dev) if want_cdf else None
+    merged = torch.empty((B, n + N), dtype=torch.float32, device=dev) if want_merged else None
+    call("nmx_sample_pdf_fwd", ptr(z), ptr(w), ptr(u), ptr(c_in), f32(eps), ptr(z_imp), ptr(inds), ptr(cdf_out),
+         ptr(merged), i64(B), i32(n), i32(N), stream())
+    return {"z_imp": z_imp, "inds": inds, "cdf": cdf_out, "z_merged": merged}
+
+
+def sort_merge_z(a, b):
+    a, b = _f32c(a), _f32c(b)
+    require_cuda(a, b)
+    B = a.shape[0]
+    out = torch.empty((B, a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    call("nmx_sort_merge_z", ptr(a), ptr(b), ptr(out), i64(B), i32(a.shape[1]), i32(b.shape[1]), stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------- loss / optimiser
+def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
+    pred, target = _f32c(pred), _f32c(target)
+    require_cuda(pred, target)
+    loss = torch.zeros((1,), dtype=torch.float32, device=pred.device)
+    d = torch.empty_like(pred) if want_grad else None
+    call("nmx_mse_fwd_bwd", ptr(pred), ptr(target), ptr(loss), ptr(d), i64(pred.numel()), f32(grad_scale), stream())
+    return loss, d
+
+
+def adam_step(p, g, m, v, lr, b1=0.9, b2=0.999, eps=1e-8, bias_correction=False, t=1):
+    require_cuda(p, g, m, v)
+    call("nmx_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), i64(p.numel()), f32(lr), f32(b1), f32(b2), f32(eps),
+         i32(1 if bias_correction else 0), i64(t), stream())
+
+
+# ----------------------------------------------------------------------------------------- GEMM building blocks
+def gemm_bf16(A, B, bias=None, relu=False, out_fp32=False):
+    """D = act(A @ B.T + bias); A [M,K] bf16, B [N,K] bf16 (tcgen05 kernel; unit-test hook)."""
+    require_cuda(A, B, bias)
+    M, K = A.shape
+    N = B.shape[0]
+    D = torch.empty((M, N), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=A.device)
+    call("nmx_gemm_bf16", ptr(A), ptr(B), ptr(bias), ptr(D), i64(M), i32(N), i32(K), i32(1 if relu else 0),
+         i32(1 if out_fp32 else 0), stream())
+    return D
+
+
+def wgrad_bf16(dY, X):
+    """dW[M,N] = dY[P,M].T @ X[P,N] in fp32 (tcgen05 kernel, MN-major operands; unit-test hook)."""
+    require_cuda(dY, X)
+    P, M = dY.shape
+    N = X.shape[1]
+    dW = torch.zeros((M, N), dtype=torch.float32, device=dY.device)
+    call("nmx_wgrad_bf16", ptr(dY), ptr(X), ptr(dW), i64(P), i32(M), i32(N), stream())
+    return dW
+
+
+def colsum_bf16(Y):
+    require_cuda(Y)
+    P, N = Y.shape
+    out = torch.zeros((N,), dtype=torch.float32, device=Y.device)
+    call("nmx_colsum_bf16", ptr(Y), ptr(out), i64(P), i32(N), stream())
+    return out

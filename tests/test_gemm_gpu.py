@@ -1,0 +1,49 @@
+"""tcgen05 GEMM building blocks vs torch fp32 matmul of the same bf16 operands (floating-point kernel:
+torch fp32 reference, tolerance = bf16 output rounding)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from nerf_meets_mlx_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (1000, 256, 320), (128 * 150 + 17, 256, 256),
+                                   (4096, 128, 320), (300, 64, 128), (5, 32, 64)])
+def test_gemm_kmajor(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().T + bias
+    out = ops.gemm_bf16(A, B, bias, relu=False, out_fp32=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), (out - ref).abs().max().item()
+    out = ops.gemm_bf16(A, B, bias, relu=True, out_fp32=False)
+    refb = torch.relu(ref)
+    assert torch.allclose(out.float(), refb, rtol=1e-2, atol=1e-2), (out.float() - refb).abs().max().item()
+
+
+@pytest.mark.parametrize("P,M,N", [(64, 128, 64), (128, 128, 256), (1000, 256, 256), (70000, 256, 256),
+                                   (4100, 128, 64), (333, 256, 128)])
+def test_wgrad_mnmajor(ops, P, M, N):
+    torch.manual_seed(P + M + N)
+    dY = (torch.randn(P, M, device="cuda") * 0.2).bfloat16()
+    X = (torch.randn(P, N, device="cuda") * 0.5).bfloat16()
+    ref = dY.float().T @ X.float()
+    out = ops.wgrad_bf16(dY, X)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3 * scale), ((out - ref).abs().max().item(), scale)
+
+
+def test_colsum(ops):
+    torch.manual_seed(0)
+    Y = torch.randn(10007, 256, device="cuda").bfloat16()
+    ref = Y.float().sum(0)
+    out = ops.colsum_bf16(Y)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-2)
