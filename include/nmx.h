@@ -114,10 +114,7 @@ typedef struct {
   int out_ch;         /* no-view head output channels (channel_output) */
   int skip_layer;     /* index i such that [input_pos, h] is concatenated after layer i; -1 = none */
   int use_viewdirs;   /* 1 = view-dir head (rgb,alpha), 0 = output_linear */
-  int enc_kind;       /* how the kernel generates inputs: 0 = rows of a precomputed fp32 [P, in_pos+in_dir] tensor,
-                         1 = Embedder PE fused in the operand producer from rays/z (n_freqs_pos / n_freqs_dir),
-                         2 = SinusoidalEncoding fused from x [P, in_dim] and bands */
-  int n_freqs_pos, n_freqs_dir;
+  int n_freqs_pos, n_freqs_dir; /* encoder bands, used by the fused input encoders (enc_kind 1 / 2 below) */
 } nmx_mlp_config;
 
 int64_t nmx_mlp_param_count(const nmx_mlp_config* cfg);
@@ -128,17 +125,21 @@ int64_t nmx_mlp_workspace_bytes(const nmx_mlp_plan* plan, int training);
 /* refresh the bf16 operand copies of the weights from fp32 params (call after every optimiser step) */
 int nmx_mlp_load_params(nmx_mlp_plan* plan, const float* params, void* workspace, void* stream);
 
-/* NeRF.forward via run_model (models/NeRF.py:25-48,201-243).
- *   enc_kind 0: x [P, in_pos+in_dir] fp32 (already encoded).
+/* NeRF.forward via run_model (models/NeRF.py:25-48,201-243).  `params` = packed fp32 parameters (biases and the
+ * tiny rgb/alpha/output heads are read from it directly; the bf16 operand copies come from nmx_mlp_load_params).
+ * enc_kind selects how the bf16 operand tile is produced:
+ *   enc_kind 0: x [P, in_pos+in_dir] fp32 (already encoded); P = B*n.
  *   enc_kind 1: rays [B, ray_stride] (o, d, near, far, viewdirs at the last 3 cols), z [B, n]; P = B*n.
- *   enc_kind 2: x [P, in_dim] raw coordinates, bands [n_freqs_pos].
- * out [P, out_cols] fp32 (out_cols = 4 for the view-dir head, out_ch otherwise).
- * save_activations != 0 keeps what nmx_mlp_bwd needs in the workspace. */
-int nmx_mlp_fwd(nmx_mlp_plan* plan, void* workspace, const float* x_or_rays, int ray_stride, const float* z,
-                const float* bands, float* out, int64_t B, int n, int save_activations, void* stream);
-/* gradients of all parameters (packed like `params`, fp32, overwritten) from d_out [P, out_cols]. */
-int nmx_mlp_bwd(nmx_mlp_plan* plan, void* workspace, const float* x_or_rays, int ray_stride, const float* z,
-                const float* bands, const float* d_out, float* d_params, int64_t B, int n, void* stream);
+ *   enc_kind 2: x [P, in_dim] raw coordinates, bands [n_freqs_pos]; P = B*n.
+ * out [P, out_cols] fp32 (out_cols = 4 (rgb, sigma) for the view-dir head, out_ch otherwise).
+ * save_activations != 0 keeps what nmx_mlp_bwd needs in the workspace (sized with training = 1). */
+int nmx_mlp_fwd(nmx_mlp_plan* plan, void* workspace, const float* params, int enc_kind, const float* x_or_rays,
+                int ray_stride, const float* z, const float* bands, float* out, int64_t B, int n,
+                int save_activations, void* stream);
+/* gradients of all parameters (packed like `params`, fp32, overwritten) from d_out [P, out_cols], using the
+ * activations saved by the preceding nmx_mlp_fwd(save_activations = 1) on the same workspace. */
+int nmx_mlp_bwd(nmx_mlp_plan* plan, void* workspace, const float* params, const float* d_out, float* d_params,
+                int64_t P, void* stream);
 
 /* generic bf16 GEMM building block on tcgen05 (exposed for unit tests / profiling):
  * D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]);  A,B bf16 row-major (K-major), D bf16 or fp32. */

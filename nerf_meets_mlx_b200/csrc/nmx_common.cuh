@@ -11,6 +11,8 @@ namespace nmx {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// NMX_DEBUG_SYNC=1: synchronise after every launch and report the failing call site (debug builds of a run only)
+int debug_sync(const char* func, int line);
 
 #define NMX_CHECK_ARG(cond, msg)                              \
   do {                                                        \
@@ -37,6 +39,7 @@ void count_launch(int n = 1);
       return (int)_e;                                                                     \
     }                                                                                     \
     ::nmx::count_launch();                                                                \
+    { int _d = ::nmx::debug_sync(__func__, __LINE__); if (_d) return _d; }                \
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200

@@ -1,5 +1,6 @@
 // libnmx core: error state, launch counter, sampling (K1) and stand-alone positional encodings (K2a/K2b).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "nmx_common.cuh"
@@ -15,6 +16,21 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int debug_sync(const char* func, int line) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("NMX_DEBUG_SYNC");
+    enabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!enabled) return 0;
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    set_error("%s:%d: kernel failed: %s", func, line, cudaGetErrorString(err));
+    fprintf(stderr, "[nmx] %s:%d: kernel failed: %s\n", func, line, cudaGetErrorString(err));
+    return (int)err;
+  }
+  return 0;
+}
 }  // namespace nmx
 
 using namespace nmx;

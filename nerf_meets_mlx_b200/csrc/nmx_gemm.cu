@@ -14,6 +14,7 @@
 
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
+#include "nmx_gemm.cuh"
 
 using namespace nmx;
 using namespace nmx::sm100;
@@ -261,6 +262,7 @@ struct WgradArgs {
   int M, N;           // M = 128 per CTA m-tile (grid.y tiles), N multiple of 64, <= 256
   float* dW;          // fp32 [M_total, ldw], accumulated with atomics at column offset w_col
   int ldw, w_col;
+  int n_valid;        // only columns < n_valid are accumulated (padded K inputs)
   int kb_per_cta;     // 64-point blocks per CTA
 };
 
@@ -370,7 +372,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       tmem_ld_wait();
       if (m < args.M) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < args.n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
       }
     }
   }
@@ -413,16 +416,6 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, int ld, int col0, int N,
 namespace nmx {
 
 // Host-side launchers (internal C++ API used by nmx_mlp.cu and the C ABI test hook).
-struct GemmDesc {
-  const void* A0; int64_t a0_rows; int a0_cols, a0_ld, a0_col, a0_k;
-  const void* A1; int a1_cols, a1_ld, a1_col, a1_k;   // A1 may be null
-  const void* B; int b_rows, b_cols, b_ld, b_col;     // B: [N, K] row-major bf16
-  int64_t M; int N;
-  const float* bias; void* D; int ldd; int out_fp32; int relu;
-  const void* mask; int ldmask;
-  const float* row_vec; int row_stride; const float* col_vec;
-};
-
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
   if (g.N % 32 != 0 || g.N < 32 || g.N > 256) { set_error("gemm: N must be a multiple of 32 in [32,256] (got %d)", g.N); return NMX_E_BADARG; }
@@ -459,23 +452,17 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   return 0;
 }
 
-struct WgradDesc {
-  const void* dY; int dy_cols, dy_ld, dy_col;   // [P, dy_cols] bf16
-  const void* X; int x_cols, x_ld, x_col;       // [P, x_cols] bf16
-  int64_t P; int M, N;                          // M multiple of 128, N multiple of 64 (<= 256)
-  float* dW; int ldw, w_col;
-};
-
 int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   if (g.P <= 0) return 0;
-  if (g.M % 128 || g.N % 64 || g.N > 256 || g.N <= 0) { set_error("wgrad: M %% 128, N %% 64, N <= 256 required (M=%d N=%d)", g.M, g.N); return NMX_E_BADARG; }
+  if (g.M % 64 || g.M <= 0 || g.N % 64 || g.N > 256 || g.N <= 0) { set_error("wgrad: M %% 64, N %% 64, N <= 256 required (M=%d N=%d)", g.M, g.N); return NMX_E_BADARG; }
   CUtensorMap tDY, tX;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tDY, g.dY, g.P, g.dy_cols, g.dy_ld, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tX, g.X, g.P, g.x_cols, g.x_ld, 64))) return rc;
   WgradArgs a;
   a.dy_col = g.dy_col; a.x_col = g.x_col; a.P = (int)g.P; a.M = g.M; a.N = g.N; a.dW = g.dW; a.ldw = g.ldw; a.w_col = g.w_col;
-  int m_tiles = g.M / 128;
+  a.n_valid = g.n_valid > 0 ? g.n_valid : g.N;
+  int m_tiles = (g.M + 127) / 128;
   int total_kb = (int)((g.P + 63) / 64);
   int splits = kNumSMs / m_tiles;
   if (splits > total_kb) splits = total_kb;
@@ -517,7 +504,7 @@ extern "C" int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, int64_t 
   nmx::WgradDesc g{};
   g.dY = dY; g.dy_cols = M; g.dy_ld = M; g.dy_col = 0;
   g.X = X; g.x_cols = N; g.x_ld = N; g.x_col = 0;
-  g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = N; g.w_col = 0;
+  g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = N; g.w_col = 0; g.n_valid = N;
   return nmx::launch_wgrad(g, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,31 @@
+// Internal C++ API of the tcgen05 GEMM building blocks (nmx_gemm.cu), used by nmx_mlp.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nmx {
+
+// D[M,N] = epi(A[M,K] * B[N,K]^T); A = K-concatenation of up to two row-major bf16 tensors.
+struct GemmDesc {
+  const void* A0; int64_t a0_rows; int a0_cols, a0_ld, a0_col, a0_k;
+  const void* A1; int a1_cols, a1_ld, a1_col, a1_k;   // A1 may be null
+  const void* B; int b_rows, b_cols, b_ld, b_col;     // B: [N, K] row-major bf16
+  int64_t M; int N;
+  const float* bias; void* D; int ldd; int out_fp32; int relu;
+  const void* mask; int ldmask;                       // output *= (mask > 0)
+  const float* row_vec; int row_stride; const float* col_vec;  // + row_vec[m] * col_vec[n] before the mask
+};
+
+// dW[M, w_col + (0..n_valid)) += dY[P, dy_col + (0..M))^T * X[P, x_col + (0..N))
+struct WgradDesc {
+  const void* dY; int dy_cols, dy_ld, dy_col;
+  const void* X; int x_cols, x_ld, x_col;
+  int64_t P; int M, N;                                // M % 64 == 0, N % 64 == 0 (<= 256)
+  float* dW; int ldw, w_col; int n_valid;             // only columns < n_valid are accumulated
+};
+
+int launch_gemm(const GemmDesc& g, cudaStream_t stream);
+int launch_wgrad(const WgradDesc& g, cudaStream_t stream);
+int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out, cudaStream_t stream);
+
+}  // namespace nmx

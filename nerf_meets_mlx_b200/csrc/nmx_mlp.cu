@@ -1,0 +1,661 @@
+// K3: the NeRF MLP (models/NeRF.py:160-243) on the tcgen05 GEMM building blocks of nmx_gemm.cu.
+//
+// Forward   : encode inputs (PE generated on the fly from rays/z, never materialised in fp32) -> bf16 operand tile
+//             X0 = [PE(pos) | pad | PE(dir) | pad];  trunk layers h_l = relu(W_l [x|h] + b_l) as bf16 GEMMs with fp32
+//             accumulation in TMEM; skip concat [input_pos, h] is a K-concatenation of two TMA sources (no copy);
+//             view-dir head: feature (no act), dir layer relu, rgb/alpha heads (tiny N) on CUDA cores -> raw fp32.
+// Backward  : heads -> dir layer -> feature -> trunk, each layer = one dgrad GEMM (ReLU mask of the saved
+//             activation and the alpha rank-1 term fused in the epilogue) + one wgrad GEMM (contraction over points,
+//             MN-major operands straight from the saved row-major activations) + a column-sum for the bias.
+// Dead work skipped exactly as autograd would: no dgrad into pure-encoding inputs.
+#include <stdlib.h>
+#include <vector>
+
+#include "nmx_common.cuh"
+#include "nmx_gemm.cuh"
+
+
+using namespace nmx;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+constexpr int64_t kInferChunk = 65536;  // points per inference chunk (activations stay L2-resident)
+}  // namespace
+
+struct LinearRef {
+  int out, in;
+  int64_t w_off, b_off;  // offsets (floats) into the packed fp32 parameter buffer
+};
+
+struct nmx_mlp_plan {
+  nmx_mlp_config cfg;
+  int64_t max_points;
+  int D, W, in_pos, in_dir, pos_pad, dir_pad, x0_cols;
+  std::vector<LinearRef> trunk;  // D layers
+  LinearRef feat, alpha, dir, rgb, outl;
+  int64_t n_params;
+  // packed bf16 weights (offsets in bytes from workspace base)
+  std::vector<int64_t> wf_off, wt_off;  // forward [W, K_l] and transposed-h-part [W, W] per trunk layer
+  std::vector<int> wf_k;                // padded K of each trunk layer
+  int64_t wf_feat, wt_feat, wf_dir, wt_dir;
+  int wf_dir_k;
+  int64_t weights_bytes;
+  // activation region (offsets relative to its start; depend on capacity)
+  int64_t act_points_train, act_points_infer;
+};
+
+namespace {
+
+struct ActLayout {
+  int64_t x0, h0, feat, hd, g0, g1, ghd, dsig, total;
+  int64_t h_stride;  // bytes between consecutive saved trunk activations (0 = ping-pong of 2 buffers)
+};
+
+ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
+  ActLayout a;
+  int64_t off = 0;
+  a.x0 = off; off += align256(cap * p->x0_cols * 2);
+  int64_t hbytes = align256(cap * p->W * 2);
+  a.h0 = off;
+  a.h_stride = hbytes;
+  off += hbytes * (training ? p->D : 2);
+  a.feat = off; off += hbytes;
+  a.hd = off; off += align256(cap * (p->W / 2) * 2);
+  a.g0 = a.g1 = a.ghd = a.dsig = 0;
+  if (training) {
+    a.g0 = off; off += hbytes;
+    a.g1 = off; off += hbytes;
+    a.ghd = off; off += align256(cap * (p->W / 2) * 2);
+  }
+  a.total = off;
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// dst[r, c] (bf16, ld = dst_ld) = src[r, src_col0 + c] for c < ncols, rows < nrows (fp32 src with ld = src_ld)
+__global__ void pack_rows_kernel(const float* __restrict__ src, int src_ld, int src_col0, bf16* __restrict__ dst,
+                                 int dst_ld, int dst_col0, int nrows, int ncols) {
+  int total = nrows * ncols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r = i / ncols, c = i - r * ncols;
+    dst[(size_t)r * dst_ld + dst_col0 + c] = __float2bfloat16_rn(src[(size_t)r * src_ld + src_col0 + c]);
+  }
+}
+// dst[c, r] = src[r, src_col0 + c]  (transposed copy)
+__global__ void pack_transpose_kernel(const float* __restrict__ src, int src_ld, int src_col0, bf16* __restrict__ dst,
+                                      int dst_ld, int nrows, int ncols) {
+  int total = nrows * ncols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int c = i / nrows, r = i - c * nrows;
+    dst[(size_t)c * dst_ld + r] = __float2bfloat16_rn(src[(size_t)r * src_ld + src_col0 + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ input encoding
+// enc_kind 1: X0[p, :] = [pos(3), {sin(k^2 pos), cos(k^2 pos)}_k, 0-pad | dir PE (precomputed per ray), 0-pad]
+// One thread per (point, unit); unit u in [0, n_freqs_pos] handles the raw input (u=0) or band u-1; the last
+// units copy the per-ray view-dir encoding and write the zero padding.
+__global__ void __launch_bounds__(256)
+encode_rays_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
+                   const bf16* __restrict__ dir_pe, bf16* __restrict__ x0, int64_t p0, int64_t npts, int n,
+                   int n_freqs_pos, int in_pos, int pos_pad, int dir_pad) {
+  const int units = n_freqs_pos + 2;  // input, bands..., tail (padding + dir copy)
+  const int x0_cols = pos_pad + dir_pad;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts * units;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lp = t / units;
+    int u = (int)(t - lp * units);
+    int64_t p = p0 + lp;
+    int64_t b = p / n;
+    bf16* row = x0 + lp * x0_cols;
+    if (u == units - 1) {
+      for (int c = in_pos; c < pos_pad; ++c) row[c] = __float2bfloat16_rn(0.0f);
+      if (dir_pad > 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(dir_pe + b * dir_pad);
+        uint4* dst = reinterpret_cast<uint4*>(row + pos_pad);
+        for (int c = 0; c < dir_pad / 8; ++c) dst[c] = __ldg(src + c);
+      }
+      continue;
+    }
+    const float* r = rays + b * ray_stride;
+    float zz = z[p];
+    float px = __fadd_rn(r[0], __fmul_rn(zz, r[3]));  // pos = o + z*d (render.py:142), mul then add
+    float py = __fadd_rn(r[1], __fmul_rn(zz, r[4]));
+    float pz = __fadd_rn(r[2], __fmul_rn(zz, r[5]));
+    if (u == 0) {
+      row[0] = __float2bfloat16_rn(px);
+      row[1] = __float2bfloat16_rn(py);
+      row[2] = __float2bfloat16_rn(pz);
+    } else {
+      int k = u - 1;
+      float f = (float)(k * k);  // embedding.py:47-49: linspace(0, N-1, N) ** 2
+      float sx, cx, sy, cy, sz, cz;
+      sincosf(__fmul_rn(px, f), &sx, &cx);
+      sincosf(__fmul_rn(py, f), &sy, &cy);
+      sincosf(__fmul_rn(pz, f), &sz, &cz);
+      bf16* o = row + 3 + 6 * k;
+      o[0] = __float2bfloat16_rn(sx);
+      o[1] = __float2bfloat16_rn(sy);
+      o[2] = __float2bfloat16_rn(sz);
+      o[3] = __float2bfloat16_rn(cx);
+      o[4] = __float2bfloat16_rn(cy);
+      o[5] = __float2bfloat16_rn(cz);
+    }
+  }
+}
+
+// per-ray view-dir PE: dir_pe[b, :] = [d(3), {sin(k^2 d), cos(k^2 d)}_k, 0-pad], d = last 3 columns of the ray row
+__global__ void encode_dirs_kernel(const float* __restrict__ rays, int ray_stride, bf16* __restrict__ dir_pe, int64_t B,
+                                   int n_freqs_dir, int dir_pad) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B * dir_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = t / dir_pad;
+    int c = (int)(t - b * dir_pad);
+    const float* d = rays + b * ray_stride + (ray_stride - 3);
+    float v = 0.0f;
+    int in_dir = 3 + 6 * n_freqs_dir;
+    if (c < 3) v = d[c];
+    else if (c < in_dir) {
+      int q = c - 3, k = q / 6, rr = q - 6 * k, fn = rr / 3, dd = rr - 3 * fn;
+      float a = __fmul_rn(d[dd], (float)(k * k));
+      v = fn ? cosf(a) : sinf(a);
+    }
+    dir_pe[t] = __float2bfloat16_rn(v);
+  }
+}
+
+// enc_kind 0: X0[p, :] = [x[p, 0:in_pos], 0-pad | x[p, in_pos:in_pos+in_dir], 0-pad]  (already-encoded fp32 input)
+__global__ void encode_copy_kernel(const float* __restrict__ x, bf16* __restrict__ x0, int64_t p0, int64_t npts,
+                                   int in_pos, int in_dir, int pos_pad, int dir_pad) {
+  const int cols = pos_pad + dir_pad;
+  const int in_tot = in_pos + in_dir;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts * cols;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lp = t / cols;
+    int c = (int)(t - lp * cols);
+    float v = 0.0f;
+    if (c < in_pos) v = x[(p0 + lp) * in_tot + c];
+    else if (c >= pos_pad && c - pos_pad < in_dir) v = x[(p0 + lp) * in_tot + in_pos + (c - pos_pad)];
+    x0[t] = __float2bfloat16_rn(v);
+  }
+}
+
+// enc_kind 2: SinusoidalEncoding (encoding/sinusoidal.py:49-66) of raw coords x [P, in_dim] with bands[n_freqs]
+__global__ void encode_sinusoidal_kernel(const float* __restrict__ x, const float* __restrict__ bands,
+                                         bf16* __restrict__ x0, int64_t p0, int64_t npts, int in_dim, int n_freqs,
+                                         int pos_pad) {
+  const float half_pi = 1.57079637050628662109375f;
+  const int half = in_dim * n_freqs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts * pos_pad;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lp = t / pos_pad;
+    int c = (int)(t - lp * pos_pad);
+    float v = 0.0f;
+    if (c < 2 * half) {
+      int q = c < half ? c : c - half;
+      int d = q / n_freqs, k = q - d * n_freqs;
+      float s = __fmul_rn(x[(p0 + lp) * in_dim + d], bands[k]);
+      if (c >= half) s = __fadd_rn(s, half_pi);
+      v = sinf(s);
+    }
+    x0[t] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small heads
+// out[p, col0 + o] = h[p, :] . Wt[o, :] + b[o],  o < n_out <= 8   (one warp per point, K <= 256, K % 64 == 0)
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restrict__ Wt, const float* __restrict__ b,
+                int n_out, float* __restrict__ out, int ldo, int col0, int64_t P) {
+  extern __shared__ float s_w[];  // [n_out][K]
+  for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) s_w[i] = Wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t p = warp0; p < P; p += nw) {
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
+    for (int k0 = lane * 2; k0 < K; k0 += 64) {
+      __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(h + p * ldh + k0);
+      float h0 = __bfloat162float(hv.x), h1 = __bfloat162float(hv.y);
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o < n_out) acc[o] += h0 * s_w[o * K + k0] + h1 * s_w[o * K + k0 + 1];
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (o < n_out) acc[o] = warp_sum(acc[o]);
+    if (lane < n_out) {
+      float v = 0.0f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (o == lane) v = acc[o];
+      out[p * ldo + col0 + lane] = v + b[lane];
+    }
+  }
+}
+
+// backward of a small head: d_out[p, col0 + o] given.
+//   dW[o, k] += sum_p d_out[p,o] h[p,k] ; db[o] += sum_p d_out[p,o]
+//   optionally d_h[p, k] = (sum_o d_out[p,o] W[o,k]) * (h[p,k] > 0)   (bf16; when the head input is post-ReLU)
+// Block = K threads (thread k owns column k), grid-strided over slabs of points.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restrict__ Wt, int n_out,
+                const float* __restrict__ d_out, int ldo, int col0, int64_t P, float* __restrict__ dW,
+                float* __restrict__ db, bf16* __restrict__ d_h, int ldd) {
+  const int k = threadIdx.x;
+  float w[8], acc[8], accb[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    w[o] = (o < n_out && k < K) ? Wt[o * K + k] : 0.0f;
+    acc[o] = 0.0f;
+    accb[o] = 0.0f;
+  }
+  if (k < K) {
+#pragma unroll 4
+    for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
+      float hv = __bfloat162float(h[p * ldh + k]);
+      float dh = 0.0f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (o < n_out) {
+          float d = __ldg(d_out + p * ldo + col0 + o);
+          acc[o] += d * hv;
+          if (k == 0) accb[o] += d;
+          dh += d * w[o];
+        }
+      }
+      if (d_h != nullptr) d_h[p * ldd + k] = __float2bfloat16_rn(hv > 0.0f ? dh : 0.0f);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < n_out) {
+        atomicAdd(dW + o * K + k, acc[o]);
+        if (k == 0) atomicAdd(db + o, accb[o]);
+      }
+    }
+  }
+}
+
+// unpack a padded fp32 [rows, src_ld] scratch into the packed gradient (dst ld) -- used for wgrad of padded inputs
+__global__ void add_cols_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld,
+                                int dst_col0, int rows, int ncols) {
+  int total = rows * ncols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int r = i / ncols, c = i - r * ncols;
+    dst[(size_t)r * dst_ld + dst_col0 + c] += src[(size_t)r * src_ld + c];
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ plan
+extern "C" int64_t nmx_mlp_param_count(const nmx_mlp_config* c) {
+  if (!c) return -1;
+  int64_t n = 0;
+  for (int l = 0; l < c->n_layers; ++l) {
+    int in = (l == 0) ? c->in_pos : (c->skip_layer >= 0 && l == c->skip_layer + 1 ? c->width + c->in_pos : c->width);
+    n += (int64_t)c->width * in + c->width;
+  }
+  if (c->use_viewdirs) {
+    n += (int64_t)c->width * c->width + c->width;                    // feature
+    n += c->width + 1;                                               // alpha
+    n += (int64_t)(c->width / 2) * (c->width + c->in_dir) + c->width / 2;  // dir
+    n += 3 * (c->width / 2) + 3;                                     // rgb
+  } else {
+    n += (int64_t)c->out_ch * c->width + c->out_ch;
+  }
+  return n;
+}
+
+extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, nmx_mlp_plan** out) {
+  NMX_CHECK_ARG(c && out && max_points > 0, "cfg, out non-null; max_points > 0");
+  NMX_CHECK_ARG(c->n_layers >= 1 && c->n_layers <= 16, "1 <= n_layers <= 16");
+  NMX_CHECK_ARG(c->width % 64 == 0 && c->width >= 64 && c->width <= 256, "width must be 64, 128, 192 or 256");
+  NMX_CHECK_ARG(!c->use_viewdirs || c->width % 128 == 0, "view-dir head needs width 128 or 256");
+  NMX_CHECK_ARG(c->in_pos >= 1 && c->in_pos <= 256, "1 <= in_pos <= 256");
+  NMX_CHECK_ARG(c->in_dir >= 0 && c->in_dir <= 64, "0 <= in_dir <= 64");
+  NMX_CHECK_ARG(c->use_viewdirs ? c->in_dir > 0 : true, "view-dir head needs in_dir > 0");
+  NMX_CHECK_ARG(c->use_viewdirs || (c->out_ch >= 1 && c->out_ch <= 8), "1 <= out_ch <= 8");
+  NMX_CHECK_ARG(c->skip_layer < c->n_layers - 1, "skip_layer must be < n_layers - 1 (or -1)");
+  nmx_mlp_plan* p = new nmx_mlp_plan();
+  p->cfg = *c;
+  p->max_points = max_points;
+  p->D = c->n_layers;
+  p->W = c->width;
+  p->in_pos = c->in_pos;
+  p->in_dir = c->use_viewdirs ? c->in_dir : 0;
+  p->pos_pad = round_up(p->in_pos, 64);
+  p->dir_pad = p->in_dir > 0 ? round_up(p->in_dir, 64) : 0;
+  p->x0_cols = p->pos_pad + p->dir_pad;
+  int64_t off = 0;
+  auto lin = [&](int o, int i) {
+    LinearRef r;
+    r.out = o; r.in = i; r.w_off = off; off += (int64_t)o * i; r.b_off = off; off += o;
+    return r;
+  };
+  for (int l = 0; l < p->D; ++l) {
+    int in = (l == 0) ? p->in_pos : (c->skip_layer >= 0 && l == c->skip_layer + 1 ? p->W + p->in_pos : p->W);
+    p->trunk.push_back(lin(p->W, in));
+  }
+  if (c->use_viewdirs) {
+    p->feat = lin(p->W, p->W);
+    p->alpha = lin(1, p->W);
+    p->dir = lin(p->W / 2, p->W + p->in_dir);
+    p->rgb = lin(3, p->W / 2);
+  } else {
+    p->outl = lin(c->out_ch, p->W);
+  }
+  p->n_params = off;
+  // packed bf16 weights
+  int64_t wb = 0;
+  for (int l = 0; l < p->D; ++l) {
+    int k = (l == 0) ? p->pos_pad : (c->skip_layer >= 0 && l == c->skip_layer + 1 ? p->pos_pad + p->W : p->W);
+    p->wf_k.push_back(k);
+    p->wf_off.push_back(wb); wb += align256((int64_t)p->W * k * 2);
+    p->wt_off.push_back(wb); wb += align256((int64_t)p->W * p->W * 2);
+  }
+  if (c->use_viewdirs) {
+    p->wf_feat = wb; wb += align256((int64_t)p->W * p->W * 2);
+    p->wt_feat = wb; wb += align256((int64_t)p->W * p->W * 2);
+    p->wf_dir_k = p->W + p->dir_pad;
+    p->wf_dir = wb; wb += align256((int64_t)(p->W / 2) * p->wf_dir_k * 2);
+    p->wt_dir = wb; wb += align256((int64_t)p->W * (p->W / 2) * 2);
+  }
+  // scratch for padded wgrad outputs (fp32 [W, 64]) and per-ray dir PE
+  p->weights_bytes = align256(wb);
+  *out = p;
+  return 0;
+}
+
+extern "C" void nmx_mlp_plan_destroy(nmx_mlp_plan* plan) { delete plan; }
+
+namespace {
+int64_t dirpe_bytes(const nmx_mlp_plan* p) { return align256(p->max_points * (int64_t)(p->dir_pad > 0 ? p->dir_pad : 1) * 2); }
+}
+
+extern "C" int64_t nmx_mlp_workspace_bytes(const nmx_mlp_plan* p, int training) {
+  if (!p) return -1;
+  int64_t cap = training ? p->max_points : (p->max_points < kInferChunk ? p->max_points : kInferChunk);
+  return p->weights_bytes + dirpe_bytes(p) + act_layout(p, cap, training != 0).total + 1024;
+}
+
+extern "C" int nmx_mlp_load_params(nmx_mlp_plan* p, const float* params, void* workspace, void* stream_) {
+  NMX_CHECK_ARG(p && params && workspace, "plan, params, workspace non-null");
+  cudaStream_t s = (cudaStream_t)stream_;
+  uint8_t* ws = (uint8_t*)workspace;
+  NMX_CUDA(cudaMemsetAsync(ws, 0, p->weights_bytes, s));
+  const int W = p->W;
+  auto pack = [&](const float* src, int src_ld, int src_col0, int64_t dst_off, int dst_ld, int dst_col0, int rows, int cols) {
+    int total = rows * cols;
+    pack_rows_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, src_ld, src_col0, (bf16*)(ws + dst_off), dst_ld, dst_col0, rows, cols);
+    count_launch();
+  };
+  auto packT = [&](const float* src, int src_ld, int src_col0, int64_t dst_off, int dst_ld, int rows, int cols) {
+    int total = rows * cols;
+    pack_transpose_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, src_ld, src_col0, (bf16*)(ws + dst_off), dst_ld, rows, cols);
+    count_launch();
+  };
+  for (int l = 0; l < p->D; ++l) {
+    const LinearRef& r = p->trunk[l];
+    const float* w = params + r.w_off;
+    bool skip_in = (r.in == W + p->in_pos);
+    if (l == 0) {
+      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos);
+    } else if (skip_in) {
+      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos);
+      pack(w, r.in, p->in_pos, p->wf_off[l], p->wf_k[l], p->pos_pad, W, W);
+      packT(w, r.in, p->in_pos, p->wt_off[l], W, W, W);
+    } else {
+      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, W);
+      packT(w, r.in, 0, p->wt_off[l], W, W, W);
+    }
+  }
+  if (p->cfg.use_viewdirs) {
+    const float* wfe = params + p->feat.w_off;
+    pack(wfe, W, 0, p->wf_feat, W, 0, W, W);
+    packT(wfe, W, 0, p->wt_feat, W, W, W);
+    const float* wd = params + p->dir.w_off;
+    pack(wd, p->dir.in, 0, p->wf_dir, p->wf_dir_k, 0, W / 2, W);
+    pack(wd, p->dir.in, W, p->wf_dir, p->wf_dir_k, W, W / 2, p->in_dir);
+    packT(wd, p->dir.in, 0, p->wt_dir, W / 2, W / 2, W);
+  }
+  NMX_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================ forward
+namespace {
+
+struct Ctx {
+  nmx_mlp_plan* p;
+  uint8_t* ws;
+  uint8_t* act;
+  ActLayout al;
+  const float* params;
+  cudaStream_t s;
+  bool training;
+  int enc_kind;
+  bf16* X0() const { return (bf16*)(act + al.x0); }
+  bf16* H(int l) const { return (bf16*)(act + al.h0 + al.h_stride * (training ? l : (l & 1))); }
+  bf16* FEAT() const { return (bf16*)(act + al.feat); }
+  bf16* HD() const { return (bf16*)(act + al.hd); }
+  bf16* G(int i) const { return (bf16*)(act + (i ? al.g1 : al.g0)); }
+  bf16* GHD() const { return (bf16*)(act + al.ghd); }
+};
+
+int encode_chunk(const Ctx& c, const float* x_or_rays, int ray_stride, const float* z, const float* bands, int64_t p0,
+                 int64_t npts, int n) {
+  nmx_mlp_plan* p = c.p;
+  int kind = c.enc_kind;
+  if (kind == 1) {
+    int units = p->cfg.n_freqs_pos + 2;
+    int blocks = grid_for(npts * units, 256, 16);
+    encode_rays_kernel<<<blocks, 256, 0, c.s>>>(x_or_rays, ray_stride, z, (const bf16*)(c.ws + p->weights_bytes), c.X0(),
+                                                p0, npts, n, p->cfg.n_freqs_pos, p->in_pos, p->pos_pad, p->dir_pad);
+  } else if (kind == 2) {
+    int in_dim = p->in_pos / (2 * p->cfg.n_freqs_pos);
+    encode_sinusoidal_kernel<<<grid_for(npts * p->pos_pad, 256, 16), 256, 0, c.s>>>(
+        x_or_rays, bands, c.X0(), p0, npts, in_dim, p->cfg.n_freqs_pos, p->pos_pad);
+  } else {
+    encode_copy_kernel<<<grid_for(npts * p->x0_cols, 256, 16), 256, 0, c.s>>>(x_or_rays, c.X0(), p0, npts, p->in_pos,
+                                                                            p->in_dir, p->pos_pad, p->dir_pad);
+  }
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+int forward_chunk(const Ctx& c, int64_t npts, float* out, int out_cols) {
+  nmx_mlp_plan* p = c.p;
+  const int W = p->W;
+  int rc;
+  for (int l = 0; l < p->D; ++l) {
+    GemmDesc g{};
+    bool skip_in = (p->trunk[l].in == W + p->in_pos);
+    if (l == 0) {
+      g.A0 = c.X0(); g.a0_cols = p->x0_cols; g.a0_ld = p->x0_cols; g.a0_col = 0; g.a0_k = p->pos_pad;
+    } else if (skip_in) {
+      g.A0 = c.X0(); g.a0_cols = p->x0_cols; g.a0_ld = p->x0_cols; g.a0_col = 0; g.a0_k = p->pos_pad;
+      g.A1 = c.H(l - 1); g.a1_cols = W; g.a1_ld = W; g.a1_col = 0; g.a1_k = W;
+    } else {
+      g.A0 = c.H(l - 1); g.a0_cols = W; g.a0_ld = W; g.a0_col = 0; g.a0_k = W;
+    }
+    g.a0_rows = npts;
+    g.B = c.ws + p->wf_off[l]; g.b_rows = W; g.b_cols = p->wf_k[l]; g.b_ld = p->wf_k[l]; g.b_col = 0;
+    g.M = npts; g.N = W; g.bias = c.params + p->trunk[l].b_off; g.D = c.H(l); g.ldd = W; g.relu = 1;
+    if ((rc = launch_gemm(g, c.s))) return rc;
+  }
+  const bf16* hl = c.H(p->D - 1);
+  if (p->cfg.use_viewdirs) {
+    // alpha head (NeRF.py:230) -> raw[:, 3]
+    head_fwd_kernel<<<grid_for(npts, 8, 16), 256, W * sizeof(float), c.s>>>(hl, W, W, c.params + p->alpha.w_off,
+                                                                           c.params + p->alpha.b_off, 1, out, out_cols, 3, npts);
+    NMX_LAUNCH_CHECK();
+    // feature (no activation, NeRF.py:231)
+    GemmDesc g{};
+    g.A0 = hl; g.a0_rows = npts; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
+    g.B = c.ws + p->wf_feat; g.b_rows = W; g.b_cols = W; g.b_ld = W;
+    g.M = npts; g.N = W; g.bias = c.params + p->feat.b_off; g.D = c.FEAT(); g.ldd = W; g.relu = 0;
+    if ((rc = launch_gemm(g, c.s))) return rc;
+    // dir layer on [feature, input_dir] (NeRF.py:232-236)
+    GemmDesc d{};
+    d.A0 = c.FEAT(); d.a0_rows = npts; d.a0_cols = W; d.a0_ld = W; d.a0_k = W;
+    d.A1 = c.X0(); d.a1_cols = p->x0_cols; d.a1_ld = p->x0_cols; d.a1_col = p->pos_pad; d.a1_k = p->dir_pad;
+    d.B = c.ws + p->wf_dir; d.b_rows = W / 2; d.b_cols = p->wf_dir_k; d.b_ld = p->wf_dir_k;
+    d.M = npts; d.N = W / 2; d.bias = c.params + p->dir.b_off; d.D = c.HD(); d.ldd = W / 2; d.relu = 1;
+    if ((rc = launch_gemm(d, c.s))) return rc;
+    // rgb head (NeRF.py:238) -> raw[:, 0:3]
+    head_fwd_kernel<<<grid_for(npts, 8, 16), 256, 3 * (W / 2) * sizeof(float), c.s>>>(
+        c.HD(), W / 2, W / 2, c.params + p->rgb.w_off, c.params + p->rgb.b_off, 3, out, out_cols, 0, npts);
+    NMX_LAUNCH_CHECK();
+  } else {
+    head_fwd_kernel<<<grid_for(npts, 8, 16), 256, p->cfg.out_ch * W * sizeof(float), c.s>>>(
+        hl, W, W, c.params + p->outl.w_off, c.params + p->outl.b_off, p->cfg.out_ch, out, out_cols, 0, npts);
+    NMX_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
+                           const float* x_or_rays, int ray_stride, const float* z, const float* bands, float* out,
+                           int64_t B, int n, int save_activations, void* stream_) {
+  NMX_CHECK_ARG(p && workspace && params && x_or_rays && out, "plan, workspace, params, input, out non-null");
+  NMX_CHECK_ARG(B >= 0 && n >= 1, "B >= 0, n >= 1");
+  const int64_t P = B * n;
+  if (P == 0) return 0;
+  NMX_CHECK_ARG(P <= p->max_points, "B*n exceeds the plan's max_points");
+  NMX_CHECK_ARG(enc_kind >= 0 && enc_kind <= 2, "enc_kind in {0,1,2}");
+  NMX_CHECK_ARG(enc_kind != 1 || (z != nullptr && ray_stride >= 9), "enc_kind 1 needs z and ray_stride >= 9");
+  NMX_CHECK_ARG(enc_kind != 1 || (p->in_pos == 3 + 6 * p->cfg.n_freqs_pos && (p->in_dir == 0 || p->in_dir == 3 + 6 * p->cfg.n_freqs_dir)),
+                "enc_kind 1 needs in_pos == 3+6*n_freqs_pos and in_dir == 3+6*n_freqs_dir");
+  NMX_CHECK_ARG(enc_kind != 2 || (bands != nullptr && p->cfg.n_freqs_pos > 0 && p->in_pos % (2 * p->cfg.n_freqs_pos) == 0),
+                "enc_kind 2 needs bands and in_pos == 2*in_dim*n_freqs_pos");
+  Ctx c;
+  c.p = p; c.ws = (uint8_t*)workspace; c.params = params; c.s = (cudaStream_t)stream_; c.training = save_activations != 0;
+  c.act = c.ws + p->weights_bytes + dirpe_bytes(p);
+  const int out_cols = p->cfg.use_viewdirs ? 4 : p->cfg.out_ch;
+  int rc;
+  c.enc_kind = enc_kind;
+  if (enc_kind == 1 && p->dir_pad > 0) {
+    encode_dirs_kernel<<<grid_for(B * p->dir_pad, 256, 8), 256, 0, c.s>>>(x_or_rays, ray_stride,
+                                                                          (bf16*)(c.ws + p->weights_bytes), B,
+                                                                          p->cfg.n_freqs_dir, p->dir_pad);
+    NMX_LAUNCH_CHECK();
+  }
+  if (c.training) {
+    c.al = act_layout(p, p->max_points, true);
+    if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
+    return forward_chunk(c, P, out, out_cols);
+  }
+  int64_t cap = p->max_points < kInferChunk ? p->max_points : kInferChunk;
+  c.al = act_layout(p, cap, false);
+  for (int64_t p0 = 0; p0 < P; p0 += cap) {
+    int64_t npts = P - p0 < cap ? P - p0 : cap;
+    if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
+    if ((rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols))) return rc;
+  }
+  return 0;
+}
+
+// ================================================================================================ backward
+extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params, const float* d_out,
+                           float* d_params, int64_t P, void* stream_) {
+  NMX_CHECK_ARG(p && workspace && params && d_out && d_params, "plan, workspace, params, d_out, d_params non-null");
+  NMX_CHECK_ARG(P >= 0 && P <= p->max_points, "0 <= P <= max_points");
+  cudaStream_t s = (cudaStream_t)stream_;
+  NMX_CUDA(cudaMemsetAsync(d_params, 0, p->n_params * sizeof(float), s));
+  if (P == 0) return 0;
+  Ctx c;
+  c.p = p; c.ws = (uint8_t*)workspace; c.params = params; c.s = s; c.training = true;
+  c.act = c.ws + p->weights_bytes + dirpe_bytes(p);
+  c.al = act_layout(p, p->max_points, true);
+  const int W = p->W;
+  const int out_cols = p->cfg.use_viewdirs ? 4 : p->cfg.out_ch;
+  int rc;
+  int cur = 0;  // index of the gradient buffer holding dY of the layer being processed
+  const bf16* hl = c.H(p->D - 1);
+  const int hb_blocks = kNumSMs * 4;
+
+  auto wgrad = [&](const bf16* dY, int dy_cols, const bf16* X, int x_cols, int x_col, int M, int N, int n_valid,
+                   float* dW, int ldw, int w_col) {
+    WgradDesc g{};
+    g.dY = dY; g.dy_cols = dy_cols; g.dy_ld = dy_cols; g.dy_col = 0;
+    g.X = X; g.x_cols = x_cols; g.x_ld = x_cols; g.x_col = x_col;
+    g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid;
+    return launch_wgrad(g, s);
+  };
+
+  if (getenv("NMX_DEBUG_SYNC")) {
+    cudaError_t e0 = cudaDeviceSynchronize();
+    fprintf(stderr, "[nmx] bwd entry sync: %s | ws=%p act=%p params=%p d_out=%p d_params=%p P=%lld HD=%p GHD=%p hl=%p\n",
+            cudaGetErrorString(e0), (void*)c.ws, (void*)c.act, (const void*)params, (const void*)d_out, (void*)d_params,
+            (long long)P, (void*)c.HD(), (void*)c.GHD(), (const void*)hl);
+  }
+  if (p->cfg.use_viewdirs) {
+    // rgb head: d_hd_pre = (d_rgb W_rgb) * [hd > 0]; dW_rgb, db_rgb
+    head_bwd_kernel<<<hb_blocks, W / 2 < 32 ? 32 : W / 2, 0, s>>>(c.HD(), W / 2, W / 2, params + p->rgb.w_off, 3, d_out,
+                                                                  out_cols, 0, P, d_params + p->rgb.w_off,
+                                                                  d_params + p->rgb.b_off, c.GHD(), W / 2);
+    NMX_LAUNCH_CHECK();
+    // alpha head: dW_alpha, db_alpha (its d_h is the rank-1 term of the feature dgrad epilogue)
+    head_bwd_kernel<<<hb_blocks, W, 0, s>>>(hl, W, W, params + p->alpha.w_off, 1, d_out, out_cols, 3, P,
+                                            d_params + p->alpha.w_off, d_params + p->alpha.b_off, nullptr, 0);
+    NMX_LAUNCH_CHECK();
+    // dir layer: wgrad over [feature | dir PE], bias, dgrad to feature
+    float* dWd = d_params + p->dir.w_off;
+    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0))) return rc;
+    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W))) return rc;
+    if ((rc = launch_colsum(c.GHD(), W / 2, 0, W / 2, P, d_params + p->dir.b_off, s))) return rc;
+    GemmDesc g{};
+    g.A0 = c.GHD(); g.a0_rows = P; g.a0_cols = W / 2; g.a0_ld = W / 2; g.a0_k = W / 2;
+    g.B = c.ws + p->wt_dir; g.b_rows = W; g.b_cols = W / 2; g.b_ld = W / 2;
+    g.M = P; g.N = W; g.D = c.G(0); g.ldd = W;
+    if ((rc = launch_gemm(g, s))) return rc;
+    // feature layer: wgrad, bias, dgrad (+ alpha rank-1 term, ReLU mask of h_{D-1})
+    if ((rc = wgrad(c.G(0), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0))) return rc;
+    if ((rc = launch_colsum(c.G(0), W, 0, W, P, d_params + p->feat.b_off, s))) return rc;
+    GemmDesc f{};
+    f.A0 = c.G(0); f.a0_rows = P; f.a0_cols = W; f.a0_ld = W; f.a0_k = W;
+    f.B = c.ws + p->wt_feat; f.b_rows = W; f.b_cols = W; f.b_ld = W;
+    f.M = P; f.N = W; f.D = c.G(1); f.ldd = W; f.mask = hl; f.ldmask = W;
+    f.row_vec = d_out + 3; f.row_stride = out_cols; f.col_vec = params + p->alpha.w_off;
+    if ((rc = launch_gemm(f, s))) return rc;
+    cur = 1;
+  } else {
+    // no-view head: d_h = (d_out W_out) * [h > 0]; dW_out, db_out
+    head_bwd_kernel<<<hb_blocks, W, 0, s>>>(hl, W, W, params + p->outl.w_off, p->cfg.out_ch, d_out, out_cols, 0, P,
+                                            d_params + p->outl.w_off, d_params + p->outl.b_off, c.G(0), W);
+    NMX_LAUNCH_CHECK();
+    cur = 0;
+  }
+  for (int l = p->D - 1; l >= 0; --l) {
+    const LinearRef& r = p->trunk[l];
+    const bf16* dY = c.G(cur);
+    float* dW = d_params + r.w_off;
+    bool skip_in = (r.in == W + p->in_pos);
+    if (l == 0) {
+      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0))) return rc;
+    } else if (skip_in) {
+      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0))) return rc;
+      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos))) return rc;
+    } else {
+      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0))) return rc;
+    }
+    if ((rc = launch_colsum(dY, W, 0, W, P, d_params + r.b_off, s))) return rc;
+    if (l >= 1) {
+      GemmDesc g{};
+      g.A0 = dY; g.a0_rows = P; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
+      g.B = c.ws + p->wt_off[l]; g.b_rows = W; g.b_cols = W; g.b_ld = W;
+      g.M = P; g.N = W; g.D = c.G(cur ^ 1); g.ldd = W; g.mask = c.H(l - 1); g.ldmask = W;
+      if ((rc = launch_gemm(g, s))) return rc;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}

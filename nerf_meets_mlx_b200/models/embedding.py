@@ -1,0 +1,70 @@
+"""Mirror of mlx_nerf/models/embedding.py (reference file:line in each docstring) on CUDA tensors."""
+import torch
+
+from .. import ops
+
+
+def embed(pos, embed_pos, dir, embed_dir):
+    """embedding.embed (models/embedding.py:4-21): flatten pos [B,n,3] -> PE; repeat dir per sample -> PE; concat."""
+    pos_flat = pos.reshape(-1, pos.shape[-1])
+    embedded_pos = embed_pos(pos_flat)
+    if dir is None:
+        return embedded_pos
+    dirs = dir[:, None, :].expand(-1, pos.shape[1], -1)
+    dir_flat = dirs.reshape(-1, dirs.shape[-1])
+    embedded_dir = embed_dir(dir_flat)
+    return torch.cat([embedded_pos, embedded_dir], dim=-1)
+
+
+class Embedder:
+    """Embedder (models/embedding.py:23-71).  Reference quirk kept: with log_sampling the bands are
+    linspace(0, max_freq_log2, N) ** 2 = [0, 1, 4, 9, ...] (squares, band 0 is dead)."""
+
+    def __init__(self, **kwargs) -> None:
+        self.kwargs = kwargs
+        self.create_embedding_func()
+
+    def create_embedding_func(self):
+        in_dim = self.kwargs.get("input_dims", 3)
+        self.in_dim = in_dim
+        self.include_input = bool(self.kwargs["include_input"])
+        self.n_freqs = int(self.kwargs["num_freqs"])
+        if not self.kwargs["log_sampling"]:
+            raise NotImplementedError  # embedding.py:50-51
+        max_freq = self.kwargs["max_freq_log2"]
+        if self.n_freqs > 1 and float(max_freq) != float(self.n_freqs - 1):
+            raise NotImplementedError("the fused kernels implement the reference's get_embedder bands (k^2, k < N)")
+        self.out_dim = (in_dim if self.include_input else 0) + in_dim * 2 * self.n_freqs
+
+    def embed(self, inputs):
+        return ops.pe_embedder(inputs, self.n_freqs, include_input=self.include_input)
+
+
+class _Identity:
+    n_freqs = -1
+
+    def __call__(self, x):
+        return x
+
+
+def get_embedder(n_freqs: int, /, n_input_dims: int = 3):
+    """get_embedder (models/embedding.py:73-90) -> (callable, out_dim)."""
+    if n_freqs == -1:
+        return _Identity(), 3
+    embed_kwargs = {
+        "include_input": False if 2 == n_input_dims else 3,
+        "input_dims": n_input_dims,
+        "max_freq_log2": n_freqs - 1,
+        "num_freqs": n_freqs,
+        "log_sampling": True,
+        "periodic_funcs": ["sin", "cos"],
+    }
+    embedder_obj = Embedder(**embed_kwargs)
+
+    def embedded_sample_generation_func(x, eo=embedder_obj):
+        return eo.embed(x)
+
+    embedded_sample_generation_func.n_freqs = n_freqs
+    embedded_sample_generation_func.n_input_dims = n_input_dims
+    embedded_sample_generation_func.embedder = embedder_obj
+    return embedded_sample_generation_func, embedder_obj.out_dim
