@@ -11,6 +11,7 @@
 // stage.  Warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quadrant
 // = warp_id % 4).  TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <mutex>
+#include <vector>
 
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
@@ -415,6 +416,22 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ Y, int ld, int col0, int N,
 
 namespace nmx {
 
+// ---- optional live profiling (bench.py roofline): CUDA events around every GEMM / wgrad launch on its stream
+struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static void prof_begin(int kind, double flops, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r; r.kind = kind; r.flops = flops;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+static void prof_end(cudaStream_t s) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_prof.back().b, s);
+}
+
 // Host-side launchers (internal C++ API used by nmx_mlp.cu and the C ABI test hook).
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
@@ -437,6 +454,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   a.row_stride = g.row_stride; a.col_vec = g.col_vec;
   int tiles = (int)((g.M + BM - 1) / BM);
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  prof_begin(0, 2.0 * (double)g.M * g.N * (g.a0_k + a.a1_k), stream);
   if (g.N > 128) {
     using L = GemmSmem<256, 4>;
     static bool attr = false;
@@ -448,6 +466,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
     gemm_kmajor_kernel<128, 6><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, a);
   }
+  prof_end(stream);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -471,7 +490,9 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   using L = WgradSmem<4>;
   static bool attr = false;
   if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+  prof_begin(1, 2.0 * (double)g.P * g.M * g.N, stream);
   wgrad_kernel<4><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, a);
+  prof_end(stream);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -486,6 +507,27 @@ int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out,
 }
 
 }  // namespace nmx
+
+extern "C" int nmx_profile_enable(int on) {
+  for (auto& r : nmx::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  nmx::g_prof.clear();
+  nmx::g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t* launches) {
+  NMX_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0; int64_t n = 0;
+  for (auto& r : nmx::g_prof) {
+    if (r.kind != kind) continue;
+    float t = 0; cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t; fl += r.flops; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = n;
+  return 0;
+}
 
 // C ABI test hooks -----------------------------------------------------------------------------------------------
 extern "C" int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, void* D, int64_t M, int N, int K,

@@ -99,7 +99,7 @@ __global__ void pack_transpose_kernel(const float* __restrict__ src, int src_ld,
 // units copy the per-ray view-dir encoding and write the zero padding.
 __global__ void __launch_bounds__(256)
 encode_rays_kernel(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
-                   const bf16* __restrict__ dir_pe, bf16* __restrict__ x0, int64_t p0, int64_t npts, int n,
+                   const bf16* __restrict__ dir_pe, int64_t b0, bf16* __restrict__ x0, int64_t p0, int64_t npts, int n,
                    int n_freqs_pos, int in_pos, int pos_pad, int dir_pad) {
   const int units = n_freqs_pos + 2;  // input, bands..., tail (padding + dir copy)
   const int x0_cols = pos_pad + dir_pad;
@@ -113,7 +113,7 @@ encode_rays_kernel(const float* __restrict__ rays, int ray_stride, const float* 
     if (u == units - 1) {
       for (int c = in_pos; c < pos_pad; ++c) row[c] = __float2bfloat16_rn(0.0f);
       if (dir_pad > 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(dir_pe + b * dir_pad);
+        const uint4* src = reinterpret_cast<const uint4*>(dir_pe + (b - b0) * dir_pad);
         uint4* dst = reinterpret_cast<uint4*>(row + pos_pad);
         for (int c = 0; c < dir_pad / 8; ++c) dst[c] = __ldg(src + c);
       }
@@ -147,13 +147,13 @@ encode_rays_kernel(const float* __restrict__ rays, int ray_stride, const float* 
 }
 
 // per-ray view-dir PE: dir_pe[b, :] = [d(3), {sin(k^2 d), cos(k^2 d)}_k, 0-pad], d = last 3 columns of the ray row
-__global__ void encode_dirs_kernel(const float* __restrict__ rays, int ray_stride, bf16* __restrict__ dir_pe, int64_t B,
-                                   int n_freqs_dir, int dir_pad) {
+__global__ void encode_dirs_kernel(const float* __restrict__ rays, int ray_stride, bf16* __restrict__ dir_pe, int64_t b0,
+                                   int64_t B, int n_freqs_dir, int dir_pad) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B * dir_pad;
        t += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = t / dir_pad;
     int c = (int)(t - b * dir_pad);
-    const float* d = rays + b * ray_stride + (ray_stride - 3);
+    const float* d = rays + (b0 + b) * ray_stride + (ray_stride - 3);
     float v = 0.0f;
     int in_dir = 3 + 6 * n_freqs_dir;
     if (c < 3) v = d[c];
@@ -375,12 +375,20 @@ extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, 
 extern "C" void nmx_mlp_plan_destroy(nmx_mlp_plan* plan) { delete plan; }
 
 namespace {
-int64_t dirpe_bytes(const nmx_mlp_plan* p) { return align256(p->max_points * (int64_t)(p->dir_pad > 0 ? p->dir_pad : 1) * 2); }
+// per-ray view-dir PE scratch: one row per ray of the current pass / inference chunk (rays <= points)
+int64_t dirpe_bytes(const nmx_mlp_plan* p) {
+  int64_t rows = p->max_points > kInferChunk ? p->max_points : kInferChunk;
+  return align256(rows * (int64_t)(p->dir_pad > 0 ? p->dir_pad : 1) * 2);
+}
 }
 
 extern "C" int64_t nmx_mlp_workspace_bytes(const nmx_mlp_plan* p, int training) {
   if (!p) return -1;
-  int64_t cap = training ? p->max_points : (p->max_points < kInferChunk ? p->max_points : kInferChunk);
+  int64_t cap = training ? p->max_points : kInferChunk;
+  if (training) {  // a training workspace also serves inference passes (chunked layout must fit)
+    int64_t ti = act_layout(p, kInferChunk, false).total, tt = act_layout(p, cap, true).total;
+    return p->weights_bytes + dirpe_bytes(p) + (ti > tt ? ti : tt) + 1024;
+  }
   return p->weights_bytes + dirpe_bytes(p) + act_layout(p, cap, training != 0).total + 1024;
 }
 
@@ -453,10 +461,17 @@ int encode_chunk(const Ctx& c, const float* x_or_rays, int ray_stride, const flo
   nmx_mlp_plan* p = c.p;
   int kind = c.enc_kind;
   if (kind == 1) {
+    const int64_t b0 = p0 / n, b1 = (p0 + npts - 1) / n;
+    bf16* dir_pe = (bf16*)(c.ws + p->weights_bytes);
+    if (p->dir_pad > 0) {
+      encode_dirs_kernel<<<grid_for((b1 - b0 + 1) * p->dir_pad, 256, 8), 256, 0, c.s>>>(
+          x_or_rays, ray_stride, dir_pe, b0, b1 - b0 + 1, p->cfg.n_freqs_dir, p->dir_pad);
+      NMX_LAUNCH_CHECK();
+    }
     int units = p->cfg.n_freqs_pos + 2;
     int blocks = grid_for(npts * units, 256, 16);
-    encode_rays_kernel<<<blocks, 256, 0, c.s>>>(x_or_rays, ray_stride, z, (const bf16*)(c.ws + p->weights_bytes), c.X0(),
-                                                p0, npts, n, p->cfg.n_freqs_pos, p->in_pos, p->pos_pad, p->dir_pad);
+    encode_rays_kernel<<<blocks, 256, 0, c.s>>>(x_or_rays, ray_stride, z, dir_pe, b0, c.X0(), p0, npts, n,
+                                                p->cfg.n_freqs_pos, p->in_pos, p->pos_pad, p->dir_pad);
   } else if (kind == 2) {
     int in_dim = p->in_pos / (2 * p->cfg.n_freqs_pos);
     encode_sinusoidal_kernel<<<grid_for(npts * p->pos_pad, 256, 16), 256, 0, c.s>>>(
@@ -529,7 +544,7 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   NMX_CHECK_ARG(B >= 0 && n >= 1, "B >= 0, n >= 1");
   const int64_t P = B * n;
   if (P == 0) return 0;
-  NMX_CHECK_ARG(P <= p->max_points, "B*n exceeds the plan's max_points");
+  NMX_CHECK_ARG(!save_activations || P <= p->max_points, "B*n exceeds the plan's max_points (training capacity)");
   NMX_CHECK_ARG(enc_kind >= 0 && enc_kind <= 2, "enc_kind in {0,1,2}");
   NMX_CHECK_ARG(enc_kind != 1 || (z != nullptr && ray_stride >= 9), "enc_kind 1 needs z and ray_stride >= 9");
   NMX_CHECK_ARG(enc_kind != 1 || (p->in_pos == 3 + 6 * p->cfg.n_freqs_pos && (p->in_dir == 0 || p->in_dir == 3 + 6 * p->cfg.n_freqs_dir)),
@@ -542,18 +557,12 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   const int out_cols = p->cfg.use_viewdirs ? 4 : p->cfg.out_ch;
   int rc;
   c.enc_kind = enc_kind;
-  if (enc_kind == 1 && p->dir_pad > 0) {
-    encode_dirs_kernel<<<grid_for(B * p->dir_pad, 256, 8), 256, 0, c.s>>>(x_or_rays, ray_stride,
-                                                                          (bf16*)(c.ws + p->weights_bytes), B,
-                                                                          p->cfg.n_freqs_dir, p->dir_pad);
-    NMX_LAUNCH_CHECK();
-  }
   if (c.training) {
     c.al = act_layout(p, p->max_points, true);
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
     return forward_chunk(c, P, out, out_cols);
   }
-  int64_t cap = p->max_points < kInferChunk ? p->max_points : kInferChunk;
+  int64_t cap = kInferChunk;
   c.al = act_layout(p, cap, false);
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t npts = P - p0 < cap ? P - p0 : cap;

@@ -50,7 +50,7 @@ class NeRF(torch.nn.Module):
 
     def __init__(self, n_layers=8, width_layers=256, channel_input=3, channel_input_views=3, channel_output=4,
                  list_skip_connection_layers=[4], is_use_view_directions=False, device="cuda", seed=None,
-                 n_freqs_pos=0, n_freqs_dir=0, max_points=1 << 20):
+                 n_freqs_pos=0, n_freqs_dir=0, max_points=1 << 16):
         super().__init__()
         self.D = n_layers
         self.W = width_layers
@@ -95,7 +95,7 @@ class NeRF(torch.nn.Module):
     def _build_views(self):
         off = 0
         self._views = {}
-        flat = self.flat.data
+        flat = self.flat.detach()  # detach() shares the version counter: in-place edits of a view mark the weights dirty
         for name, o, i in self._layer_shapes():
             w = flat[off:off + o * i].view(o, i)
             off += o * i
@@ -120,6 +120,7 @@ class NeRF(torch.nn.Module):
                 v = self._views[name]
                 v.weight.copy_(((torch.rand(o, i, generator=g) * 2 - 1) * s).to(v.weight.device))
                 v.bias.copy_(((torch.rand(o, generator=g) * 2 - 1) * s).to(v.bias.device))
+        self._packed_version = -1
 
     def named_reference_parameters(self):
         out = {}
@@ -136,6 +137,7 @@ class NeRF(torch.nn.Module):
                 if tuple(src.shape) != tuple(dst.shape):
                     raise ValueError(f"{k}: shape {tuple(src.shape)} != {tuple(dst.shape)}")
                 dst.copy_(src)
+        self.mark_params_updated()
 
     def split_flat(self, flat):
         """Views of a flat vector (e.g. a gradient) by reference parameter name."""
@@ -150,11 +152,12 @@ class NeRF(torch.nn.Module):
     # ---------------------------------------------------------------- plan / workspace
     def _ensure(self, points, training):
         lib = L.lib()
-        if self._plan is None or points > self._max_points:
+        if self._plan is None or (training and points > self._max_points):
             if self._plan is not None:
                 lib.nmx_mlp_plan_destroy(self._plan)
                 self._plan = None
-            self._max_points = max(self._max_points, int(points))
+            if training:
+                self._max_points = max(self._max_points, int(points))
             plan = ctypes.c_void_p()
             L.call("nmx_mlp_plan_create", ctypes.byref(self._cfg), L.i64(self._max_points), ctypes.byref(plan))
             self._plan = plan

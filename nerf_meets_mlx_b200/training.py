@@ -1,0 +1,124 @@
+"""The reference's training iteration (mlx_nerf/entrypoints/__test_nerf.py:47-145, 200-305) driven straight through
+the C ABI ops -- no autograd graph, no host round trip for the resampling, optional ray-sharded data parallelism
+with one NCCL all-reduce of the flat fp32 gradient per optimiser step."""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .models.NeRF import AdamMLX, create_NeRF, default_args
+
+
+def assemble_rays(rays_o, rays_d, near, far):
+    """[o, d, near, far, viewdirs] with viewdirs = d/||d|| (__test_nerf.py:57-82)."""
+    viewdirs = rays_d / torch.linalg.norm(rays_d, dim=-1, keepdim=True)
+    ones = torch.ones_like(rays_d[..., :1])
+    return torch.cat([rays_o, rays_d, near * ones, far * ones, viewdirs], dim=-1).contiguous()
+
+
+class NeRFTrainer:
+    """Coarse(+fine) NeRF trainer with the reference's semantics:
+      * coarse loss on render_rays (white_bkgd from args), fine loss on raw2outputs with white_bkgd=False (quirk);
+      * importance samples are a DETACHED input of the fine step and come from the coarse net AFTER its update;
+      * one Adam instance without bias correction updates both nets and (faithful default) shares its moments;
+      * lr = lrate * 0.1 ** (i / (lrate_decay * 1000)).
+    `reuse_coarse_forward=True` is a declared deviation that resamples from the in-step coarse forward (pre-update
+    weights) and skips the re-forward."""
+
+    def __init__(self, args=None, device="cuda", near=2.0, far=6.0, shared_adam_state=True,
+                 reuse_coarse_forward=False, process_group=None, max_rays=8192):
+        self.args = args if args is not None else default_args(N_importance=128)
+        self.device = torch.device(device)
+        self.near, self.far = float(near), float(far)
+        kw_train, _, _, opt = create_NeRF(self.args, device=device)
+        self.kw = kw_train
+        self.coarse = kw_train["network_coarse"]
+        self.fine = kw_train["network_fine"]
+        self.optimizer = AdamMLX(self.args.lrate, betas=(0.9, 0.999), shared_state=shared_adam_state)
+        self.n_samples = int(self.args.n_depth_samples)
+        self.n_importance = int(self.args.N_importance)
+        self.white_bkgd = bool(self.args.white_bkgd)
+        self.reuse_coarse_forward = reuse_coarse_forward
+        self.iteration = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._g_coarse = torch.empty_like(self.coarse.flat.data)
+        self._g_fine = torch.empty_like(self.fine.flat.data) if self.fine is not None else None
+        self.coarse.reserve(max_rays * self.n_samples, training=True)
+        if self.fine is not None:
+            self.fine.reserve(max_rays * (self.n_samples + self.n_importance), training=True)
+        if self.world > 1:
+            self.broadcast_parameters()
+
+    # ------------------------------------------------------------------ data parallel plumbing
+    def broadcast_parameters(self):
+        for m in (self.coarse, self.fine):
+            if m is not None:
+                dist.broadcast(m.flat.data, src=0, group=self.pg)
+                m.mark_params_updated()
+
+    def _allreduce_mean(self, g):
+        if self.world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            g.mul_(1.0 / self.world)
+
+    # ------------------------------------------------------------------ one optimiser step on one net
+    def _step(self, model, rays, z, target, white_bkgd, g_buf):
+        B, n = z.shape
+        raw = model._fwd_raw(1, rays, z, None, B, n, save=True)
+        rgb, _, _, weights, _ = ops.composite_fwd(raw.view(B, n, 4), z, rays[:, 3:6].contiguous(), white_bkgd=white_bkgd)
+        loss, d_rgb = ops.mse_fwd_bwd(rgb, target)
+        d_raw = ops.composite_bwd(raw.view(B, n, 4), z, rays[:, 3:6].contiguous(), d_rgb, white_bkgd=white_bkgd)
+        model._bwd_raw(d_raw.view(B * n, 4), B * n, out=g_buf)
+        self._allreduce_mean(g_buf)
+        self.optimizer.update(model, g_buf)
+        return loss, weights
+
+    def train_iteration(self, rays_o, rays_d, target, u_vals=None):
+        """One pass of the reference loop body on this rank's shard of rays.  Returns device scalars."""
+        self.iteration += 1
+        rays = assemble_rays(rays_o, rays_d, self.near, self.far)
+        B = rays.shape[0]
+        rays_d_c = rays[:, 3:6].contiguous()
+        z = ops.sample_z(rays[:, 6], rays[:, 7], self.n_samples, lindisp=bool(getattr(self.args, "lindisp", False)))
+        loss_c, weights = self._step(self.coarse, rays, z, target, self.white_bkgd, self._g_coarse)
+        out = {"loss_coarse": loss_c}
+        if self.fine is not None:
+            if not self.reuse_coarse_forward:
+                # render_rays again with the UPDATED coarse net (__test_nerf.py:270)
+                raw = self.coarse._fwd_raw(1, rays, z, None, B, self.n_samples, save=False)
+                _, _, _, weights, _ = ops.composite_fwd(raw.view(B, self.n_samples, 4), z, rays_d_c, white_bkgd=self.white_bkgd)
+            if u_vals is None:
+                u_vals = torch.rand((B, self.n_importance), device=rays.device)
+            z_fine = ops.sample_pdf(z, weights, u_vals, want_imp=False)["z_merged"]
+            loss_f, _ = self._step(self.fine, rays, z_fine, target, False, self._g_fine)  # white_bkgd=False (:106)
+            out["loss_fine"] = loss_f
+            out["z_fine"] = z_fine
+        # learning-rate decay (__test_nerf.py:302-305)
+        decay_steps = self.args.lrate_decay * 1000
+        self.optimizer.learning_rate = self.args.lrate * (0.1 ** (self.iteration / decay_steps))
+        return out
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def render_rays_eval(self, rays, u_vals=None):
+        """Coarse + fine evaluation of a ray batch (render_rays_eval, rendering/render.py:164-241) through the raw ops."""
+        B = rays.shape[0]
+        rays_d_c = rays[:, 3:6].contiguous()
+        z = ops.sample_z(rays[:, 6], rays[:, 7], self.n_samples)
+        raw = self.coarse._fwd_raw(1, rays, z, None, B, self.n_samples, save=False)
+        rgb_c, _, _, weights, _ = ops.composite_fwd(raw.view(B, self.n_samples, 4), z, rays_d_c, white_bkgd=self.white_bkgd)
+        if u_vals is None:
+            u_vals = torch.rand((B, self.n_importance), device=rays.device)
+        z_fine = ops.sample_pdf(z, weights, u_vals, want_imp=False)["z_merged"]
+        net = self.fine if self.fine is not None else self.coarse
+        n2 = z_fine.shape[1]
+        raw_f = net._fwd_raw(1, rays, z_fine, None, B, n2, save=False)
+        rgb, disp, acc, _, _ = ops.composite_fwd(raw_f.view(B, n2, 4), z_fine, rays_d_c, white_bkgd=self.white_bkgd)
+        return {"rgb_map": rgb, "disp_map": disp, "acc_map": acc, "rgb_coarse": rgb_c}
+
+
+def psnr(mse):
+    """ops/metric.py:16-18."""
+    return 10.0 * math.log10(1.0 / float(mse))

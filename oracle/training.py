@@ -82,7 +82,7 @@ def train_iteration(coarse, fine, opt, rays_o, rays_d, target, u_vals, query_fn,
     gc = _grads(coarse, lc)
     coarse.requires_grad_(False)
     opt.update(coarse, gc)
-    out = {"loss_coarse": float(lc), "grads_coarse": gc}
+    out = {"loss_coarse": float(lc.detach()), "grads_coarse": gc}
     if fine is None:
         return out
     with torch.no_grad():
@@ -96,7 +96,7 @@ def train_iteration(coarse, fine, opt, rays_o, rays_d, target, u_vals, query_fn,
     gf = _grads(fine, lf)
     fine.requires_grad_(False)
     opt.update(fine, gf)
-    out.update(loss_fine=float(lf), grads_fine=gf, z_fine=z_fine, z_imp=z_imp)
+    out.update(loss_fine=float(lf.detach()), grads_fine=gf, z_fine=z_fine, z_imp=z_imp)
     return out
 
 
