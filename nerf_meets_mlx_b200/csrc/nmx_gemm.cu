@@ -75,8 +75,8 @@ struct GemmArgs {
   int ldd;
   int out_fp32;
   int relu;
-  const __nv_bfloat16* mask;  // saved post-ReLU activation [M, ldmask]; output *= (mask > 0)
-  int ldmask;
+  int use_mask;           // output *= (mask > 0), mask = saved post-ReLU activation read through tmMask
+  int mask_col, d_col;    // first column of the mask / output tensors
   const float* row_vec;   // optional rank-1 term row_vec[m*row_stride] * col_vec[n] added before the mask
   int row_stride;
   const float* col_vec;
@@ -88,8 +88,11 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTileBytes = STAGES * kStageBytes;
-  static constexpr int kBarOff = kTileBytes;                    // full[S], empty[S], tfull[2], tempty[2]
-  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
+  static constexpr int kChunkBytes = BM * 64 * 2;               // one 128-row x 64-col bf16 chunk (SW128 box)
+  static constexpr int kOutOff = kTileBytes;                    // 2 output staging chunks (TMA store source)
+  static constexpr int kMaskOff = kOutOff + 2 * kChunkBytes;    // 2 ReLU-mask chunks (TMA load destination)
+  static constexpr int kBarOff = kMaskOff + 2 * kChunkBytes;    // full[S], empty[S], tfull[2], tempty[2], mfull[2]
+  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 6) * 8;
   static constexpr int kBiasOff = kTmemPtrOff + 16;             // bias[BN] + colvec[BN]
   static constexpr int kTotal = kBiasOff + 2 * BN * 4;
   static constexpr int kAlloc = kTotal + 1024;                  // slack for manual 1024 B alignment
@@ -103,7 +106,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                   const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                   const __grid_constant__ CUtensorMap tmMask, const GemmArgs args) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -111,6 +115,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
+  uint64_t* mfull = tempty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   float* s_bias = reinterpret_cast<float*>(smem + L::kBiasOff);
   float* s_colv = s_bias + BN;
@@ -125,6 +130,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmMask);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -134,6 +141,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+      mbar_init(&mfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -200,49 +208,99 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
   } else {
     // ================================ epilogue warps ================================
+    // TMEM -> registers (+bias, rank-1 term, ReLU / ReLU-mask) -> bf16 -> 128B-swizzled smem chunk -> TMA store.
+    // Each thread owns one tile row; a 16 B piece c of its 128 B chunk row lands at (c ^ (row & 7)) so that both the
+    // st.shared (quarter-warp = 8 rows x 8 distinct pieces) and the TMA engine see conflict-free / canonical layout.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_local = q * 32 + lane;
+    const bool leader = (threadIdx.x == kEpiWarp0 * 32);
+    uint8_t* s_out = smem + L::kOutOff;
+    uint8_t* s_mask = smem + L::kMaskOff;
+    const int nchunks = N / 64;
+    const bool use_mask = args.use_mask != 0;
+    const uint32_t swz = (uint32_t)(row_local & 7);
+    uint32_t g = 0;  // running chunk counter (selects the staging buffer and the mask barrier parity)
+    if (use_mask && leader && (int)blockIdx.x < num_tiles) {
+      mbar_arrive_expect_tx(&mfull[0], L::kChunkBytes);
+      tma_load_2d(s_mask, &tmMask, &mfull[0], args.mask_col, blockIdx.x * BM);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = tile * BM + q * 32 + lane;
+      const int row = tile * BM + row_local;
       const bool row_ok = row < args.M;
       const float rv = (args.row_vec != nullptr && row_ok) ? args.row_vec[(size_t)row * args.row_stride] : 0.0f;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + as * BN + c0 + ((uint32_t)(q * 32) << 16), r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[c0 + j] + rv * s_colv[c0 + j];
-        if (args.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (args.mask != nullptr && row_ok) {
-          const uint4* mp = reinterpret_cast<const uint4*>(args.mask + (size_t)row * args.ldmask + c0);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 m = __ldg(mp + g);
-            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (!(__bfloat162float(mb[j]) > 0.0f)) v[g * 8 + j] = 0.0f;
-          }
-        }
-        if (row_ok) {
-          if (args.out_fp32) {
+      if (args.out_fp32) {
+        // test / debug path: direct fp32 stores
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + as * BN + c0 + ((uint32_t)(q * 32) << 16), r);
+          tmem_ld_wait();
+          if (row_ok) {
             float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(args.D) + (size_t)row * args.ldd + c0);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) dp[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          } else {
-            uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(args.D) + (size_t)row * args.ldd + c0);
+            for (int k4 = 0; k4 < 8; ++k4) {
+              float v[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              dp[g] = make_uint4(pack_bf16(v[g * 8], v[g * 8 + 1]), pack_bf16(v[g * 8 + 2], v[g * 8 + 3]),
-                                 pack_bf16(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16(v[g * 8 + 6], v[g * 8 + 7]));
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(r[k4 * 4 + e]) + s_bias[c0 + k4 * 4 + e] + rv * s_colv[c0 + k4 * 4 + e];
+                v[e] = args.relu ? fmaxf(x, 0.0f) : x;
+              }
+              dp[k4] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+      } else {
+        for (int j = 0; j < nchunks; ++j, ++g) {
+          const int buf = g & 1;
+          uint8_t* so = s_out + buf * L::kChunkBytes + row_local * 128;
+          const uint8_t* sm = s_mask + buf * L::kChunkBytes + row_local * 128;
+          if (leader) tma_store_wait_read<1>();  // the store that last used s_out[buf] has finished reading it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (use_mask && leader) {  // prefetch the next mask chunk into the buffer everyone finished reading
+            int nj = j + 1, ntile = tile;
+            if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+            if (ntile < num_tiles) {
+              mbar_arrive_expect_tx(&mfull[buf ^ 1], L::kChunkBytes);
+              tma_load_2d(s_mask + (buf ^ 1) * L::kChunkBytes, &tmMask, &mfull[buf ^ 1], args.mask_col + nj * 64, ntile * BM);
+            }
+          }
+          if (use_mask) mbar_wait(&mfull[buf], (g >> 1) & 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = j * 64 + h * 32;
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + as * BN + c0 + ((uint32_t)(q * 32) << 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int p4 = 0; p4 < 4; ++p4) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = c0 + p4 * 8 + e;
+                float x = __uint_as_float(r[p4 * 8 + e]) + s_bias[c] + rv * s_colv[c];
+                v[e] = args.relu ? fmaxf(x, 0.0f) : x;
+              }
+              const uint32_t piece = ((uint32_t)(h * 4 + p4) ^ swz) << 4;
+              if (use_mask) {
+                uint4 m = *reinterpret_cast<const uint4*>(sm + piece);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (!(__bfloat162float(mb[e]) > 0.0f)) v[e] = 0.0f;
+              }
+              *reinterpret_cast<uint4*>(so + piece) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader) {
+            tma_store_2d(&tmD, s_out + buf * L::kChunkBytes, args.d_col + j * 64, tile * BM);
+            tma_store_commit();
           }
         }
       }
@@ -250,6 +308,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
+    if (leader) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -435,7 +494,7 @@ static void prof_end(cudaStream_t s) {
 // Host-side launchers (internal C++ API used by nmx_mlp.cu and the C ABI test hook).
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0) return 0;
-  if (g.N % 32 != 0 || g.N < 32 || g.N > 256) { set_error("gemm: N must be a multiple of 32 in [32,256] (got %d)", g.N); return NMX_E_BADARG; }
+  if (g.N % 64 != 0 || g.N < 64 || g.N > 256) { set_error("gemm: N must be a multiple of 64 in [64,256] (got %d)", g.N); return NMX_E_BADARG; }
   if (g.a0_k % 64 || g.a1_k % 64 || g.a0_k <= 0) { set_error("gemm: K segments must be positive multiples of 64"); return NMX_E_BADARG; }
   if (g.M > 0x7fffffff - 256) { set_error("gemm: M too large"); return NMX_E_BADARG; }
   CUtensorMap tA0, tA1, tB;
@@ -447,24 +506,36 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     tA1 = tA0;
   }
   if ((rc = make_tmap_bf16_2d(&tB, g.B, g.b_rows, g.b_cols, g.b_ld, (uint32_t)g.N))) return rc;
+  CUtensorMap tD, tM;
+  if (!g.out_fp32) {
+    if ((rc = make_tmap_bf16_2d(&tD, g.D, g.M, g.d_cols > 0 ? g.d_cols : g.N, g.ldd, BM))) return rc;
+  } else {
+    tD = tA0;
+  }
+  if (g.mask != nullptr) {
+    if (g.out_fp32) { set_error("gemm: the ReLU-mask epilogue needs bf16 output"); return NMX_E_BADARG; }
+    if ((rc = make_tmap_bf16_2d(&tM, g.mask, g.M, g.mask_cols > 0 ? g.mask_cols : g.N, g.ldmask, BM))) return rc;
+  } else {
+    tM = tA0;
+  }
   GemmArgs a;
   a.a0_col = g.a0_col; a.a0_k = g.a0_k; a.a1_col = g.a1_col; a.a1_k = (g.A1 ? g.a1_k : 0);
   a.b_col = g.b_col; a.M = (int)g.M; a.N = g.N; a.bias = g.bias; a.D = g.D; a.ldd = g.ldd; a.out_fp32 = g.out_fp32;
-  a.relu = g.relu; a.mask = (const __nv_bfloat16*)g.mask; a.ldmask = g.ldmask; a.row_vec = g.row_vec;
+  a.relu = g.relu; a.use_mask = g.mask != nullptr; a.mask_col = g.mask_col; a.d_col = g.d_col; a.row_vec = g.row_vec;
   a.row_stride = g.row_stride; a.col_vec = g.col_vec;
   int tiles = (int)((g.M + BM - 1) / BM);
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   prof_begin(0, 2.0 * (double)g.M * g.N * (g.a0_k + a.a1_k), stream);
   if (g.N > 128) {
-    using L = GemmSmem<256, 4>;
+    using L = GemmSmem<256, 3>;
     static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
-    gemm_kmajor_kernel<256, 4><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, a);
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    gemm_kmajor_kernel<256, 3><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, tD, tM, a);
   } else {
-    using L = GemmSmem<128, 6>;
+    using L = GemmSmem<128, 4>;
     static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
-    gemm_kmajor_kernel<128, 6><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, a);
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    gemm_kmajor_kernel<128, 4><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, tD, tM, a);
   }
   prof_end(stream);
   NMX_LAUNCH_CHECK();

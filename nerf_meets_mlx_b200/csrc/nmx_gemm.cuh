@@ -12,7 +12,8 @@ struct GemmDesc {
   const void* B; int b_rows, b_cols, b_ld, b_col;     // B: [N, K] row-major bf16
   int64_t M; int N;
   const float* bias; void* D; int ldd; int out_fp32; int relu;
-  const void* mask; int ldmask;                       // output *= (mask > 0)
+  int d_cols, d_col;                                  // D tensor width (0 = N) and first output column
+  const void* mask; int ldmask; int mask_cols, mask_col;  // output *= (mask > 0); mask tensor [M, mask_cols]
   const float* row_vec; int row_stride; const float* col_vec;  // + row_vec[m] * col_vec[n] before the mask
 };
 

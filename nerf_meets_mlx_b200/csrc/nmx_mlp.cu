@@ -74,22 +74,34 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// dst[r, c] (bf16, ld = dst_ld) = src[r, src_col0 + c] for c < ncols, rows < nrows (fp32 src with ld = src_ld)
-__global__ void pack_rows_kernel(const float* __restrict__ src, int src_ld, int src_col0, bf16* __restrict__ dst,
-                                 int dst_ld, int dst_col0, int nrows, int ncols) {
-  int total = nrows * ncols;
+// One launch packs every bf16 operand copy: segment t copies (optionally transposed) a [rows, cols] window of an
+// fp32 weight matrix into its padded bf16 layout.  dst[r, dst_col0 + c] = src[r, src_col0 + c], or transposed
+// dst[c, r] = src[r, src_col0 + c].
+struct PackSeg {
+  int64_t src_off;   // floats, into params
+  int64_t dst_off;   // bytes, into the workspace
+  int src_ld, src_col0, dst_ld, dst_col0, rows, cols, transpose, pad_;
+};
+constexpr int kMaxPackSegs = 48;
+struct PackTable {
+  int n;
+  PackSeg seg[kMaxPackSegs];
+};
+
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws, const PackTable tab) {
+  const PackSeg sg = tab.seg[blockIdx.y];
+  const float* src = params + sg.src_off;
+  bf16* dst = reinterpret_cast<bf16*>(ws + sg.dst_off);
+  const int total = sg.rows * sg.cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int r = i / ncols, c = i - r * ncols;
-    dst[(size_t)r * dst_ld + dst_col0 + c] = __float2bfloat16_rn(src[(size_t)r * src_ld + src_col0 + c]);
-  }
-}
-// dst[c, r] = src[r, src_col0 + c]  (transposed copy)
-__global__ void pack_transpose_kernel(const float* __restrict__ src, int src_ld, int src_col0, bf16* __restrict__ dst,
-                                      int dst_ld, int nrows, int ncols) {
-  int total = nrows * ncols;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int c = i / nrows, r = i - c * nrows;
-    dst[(size_t)c * dst_ld + r] = __float2bfloat16_rn(src[(size_t)r * src_ld + src_col0 + c]);
+    if (!sg.transpose) {
+      int r = i / sg.cols, c = i - r * sg.cols;
+      dst[(size_t)r * sg.dst_ld + sg.dst_col0 + c] = __float2bfloat16_rn(src[(size_t)r * sg.src_ld + sg.src_col0 + c]);
+    } else {
+      int c = i / sg.rows, r = i - c * sg.rows;
+      dst[(size_t)c * sg.dst_ld + r] = __float2bfloat16_rn(src[(size_t)r * sg.src_ld + sg.src_col0 + c]);
+    }
   }
 }
 
@@ -281,16 +293,6 @@ head_bwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
   }
 }
 
-// unpack a padded fp32 [rows, src_ld] scratch into the packed gradient (dst ld) -- used for wgrad of padded inputs
-__global__ void add_cols_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld,
-                                int dst_col0, int rows, int ncols) {
-  int total = rows * ncols;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int r = i / ncols, c = i - r * ncols;
-    dst[(size_t)r * dst_ld + dst_col0 + c] += src[(size_t)r * src_ld + c];
-  }
-}
-
 }  // namespace
 
 // ================================================================================================ plan
@@ -314,7 +316,7 @@ extern "C" int64_t nmx_mlp_param_count(const nmx_mlp_config* c) {
 
 extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, nmx_mlp_plan** out) {
   NMX_CHECK_ARG(c && out && max_points > 0, "cfg, out non-null; max_points > 0");
-  NMX_CHECK_ARG(c->n_layers >= 1 && c->n_layers <= 16, "1 <= n_layers <= 16");
+  NMX_CHECK_ARG(c->n_layers >= 1 && c->n_layers <= 12, "1 <= n_layers <= 12");
   NMX_CHECK_ARG(c->width % 64 == 0 && c->width >= 64 && c->width <= 256, "width must be 64, 128, 192 or 256");
   NMX_CHECK_ARG(!c->use_viewdirs || c->width % 128 == 0, "view-dir head needs width 128 or 256");
   NMX_CHECK_ARG(c->in_pos >= 1 && c->in_pos <= 256, "1 <= in_pos <= 256");
@@ -396,43 +398,39 @@ extern "C" int nmx_mlp_load_params(nmx_mlp_plan* p, const float* params, void* w
   NMX_CHECK_ARG(p && params && workspace, "plan, params, workspace non-null");
   cudaStream_t s = (cudaStream_t)stream_;
   uint8_t* ws = (uint8_t*)workspace;
-  NMX_CUDA(cudaMemsetAsync(ws, 0, p->weights_bytes, s));
+  NMX_CUDA(cudaMemsetAsync(ws, 0, p->weights_bytes, s));  // zero padding columns (1.3 MB, cheaper than tracking)
   const int W = p->W;
-  auto pack = [&](const float* src, int src_ld, int src_col0, int64_t dst_off, int dst_ld, int dst_col0, int rows, int cols) {
-    int total = rows * cols;
-    pack_rows_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, src_ld, src_col0, (bf16*)(ws + dst_off), dst_ld, dst_col0, rows, cols);
-    count_launch();
-  };
-  auto packT = [&](const float* src, int src_ld, int src_col0, int64_t dst_off, int dst_ld, int rows, int cols) {
-    int total = rows * cols;
-    pack_transpose_kernel<<<(total + 255) / 256, 256, 0, s>>>(src, src_ld, src_col0, (bf16*)(ws + dst_off), dst_ld, rows, cols);
-    count_launch();
+  PackTable tab;
+  tab.n = 0;
+  auto add = [&](int64_t src_off, int src_ld, int src_col0, int64_t dst_off, int dst_ld, int dst_col0, int rows, int cols, int tr) {
+    PackSeg& g = tab.seg[tab.n++];
+    g.src_off = src_off; g.dst_off = dst_off; g.src_ld = src_ld; g.src_col0 = src_col0; g.dst_ld = dst_ld;
+    g.dst_col0 = dst_col0; g.rows = rows; g.cols = cols; g.transpose = tr; g.pad_ = 0;
   };
   for (int l = 0; l < p->D; ++l) {
     const LinearRef& r = p->trunk[l];
-    const float* w = params + r.w_off;
     bool skip_in = (r.in == W + p->in_pos);
     if (l == 0) {
-      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos);
+      add(r.w_off, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos, 0);
     } else if (skip_in) {
-      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos);
-      pack(w, r.in, p->in_pos, p->wf_off[l], p->wf_k[l], p->pos_pad, W, W);
-      packT(w, r.in, p->in_pos, p->wt_off[l], W, W, W);
+      add(r.w_off, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos, 0);
+      add(r.w_off, r.in, p->in_pos, p->wf_off[l], p->wf_k[l], p->pos_pad, W, W, 0);
+      add(r.w_off, r.in, p->in_pos, p->wt_off[l], W, 0, W, W, 1);
     } else {
-      pack(w, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, W);
-      packT(w, r.in, 0, p->wt_off[l], W, W, W);
+      add(r.w_off, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, W, 0);
+      add(r.w_off, r.in, 0, p->wt_off[l], W, 0, W, W, 1);
     }
   }
   if (p->cfg.use_viewdirs) {
-    const float* wfe = params + p->feat.w_off;
-    pack(wfe, W, 0, p->wf_feat, W, 0, W, W);
-    packT(wfe, W, 0, p->wt_feat, W, W, W);
-    const float* wd = params + p->dir.w_off;
-    pack(wd, p->dir.in, 0, p->wf_dir, p->wf_dir_k, 0, W / 2, W);
-    pack(wd, p->dir.in, W, p->wf_dir, p->wf_dir_k, W, W / 2, p->in_dir);
-    packT(wd, p->dir.in, 0, p->wt_dir, W / 2, W / 2, W);
+    add(p->feat.w_off, W, 0, p->wf_feat, W, 0, W, W, 0);
+    add(p->feat.w_off, W, 0, p->wt_feat, W, 0, W, W, 1);
+    add(p->dir.w_off, p->dir.in, 0, p->wf_dir, p->wf_dir_k, 0, W / 2, W, 0);
+    add(p->dir.w_off, p->dir.in, W, p->wf_dir, p->wf_dir_k, W, W / 2, p->in_dir, 0);
+    add(p->dir.w_off, p->dir.in, 0, p->wt_dir, W / 2, 0, W / 2, W, 1);
   }
-  NMX_CUDA(cudaGetLastError());
+  if (tab.n > kMaxPackSegs) { set_error("too many layers for the pack table"); return NMX_E_UNSUPPORTED; }
+  pack_weights_kernel<<<dim3(32, tab.n), 256, 0, s>>>(params, ws, tab);
+  NMX_LAUNCH_CHECK();
   return 0;
 }
 
