@@ -146,8 +146,9 @@ int nmx_mlp_bwd(nmx_mlp_plan* plan, void* workspace, const float* params, const 
 int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, void* D, int64_t M, int N, int K,
                   int relu, int d_is_fp32, void* stream);
 /* dW[M,N] (fp32, accumulated: caller zeroes) += dY[P,M]^T * X[P,N]; bf16 row-major inputs, read as MN-major
- * UMMA operands (no transposes); M % 128 == 0, N % 64 == 0, N <= 256. */
-int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, int64_t P, int M, int N, void* stream);
+ * UMMA operands (no transposes); M % 64 == 0, N % 64 == 0, N <= 256.  Optional db[M] (fp32, accumulated) += column
+ * sums of dY (the bias gradient), computed by one extra N=16 MMA against a constant all-ones operand tile. */
+int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, float* db, int64_t P, int M, int N, void* stream);
 /* out[N] (fp32, accumulated) += column sums of Y[P,N] bf16 (bias gradients). */
 int nmx_colsum_bf16(const void* Y, float* out, int64_t P, int N, void* stream);
 

@@ -323,6 +323,7 @@ struct WgradArgs {
   float* dW;          // fp32 [M_total, ldw], accumulated with atomics at column offset w_col
   int ldw, w_col;
   int n_valid;        // only columns < n_valid are accumulated (padded K inputs)
+  float* db;          // optional bias gradient [M_total]: db[m] += sum_p dY[p, m] (ones-column MMA), or null
   int kb_per_cta;     // 64-point blocks per CTA
 };
 
@@ -331,7 +332,8 @@ struct WgradSmem {
   static constexpr int kABytes = 2 * 64 * 64 * 2;   // two 64(M) x 64(P) boxes
   static constexpr int kBBytes = 4 * 64 * 64 * 2;   // up to four 64(N) x 64(P) boxes
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kOnesOff = STAGES * kStageBytes;          // constant all-ones 64(N) x 64(P) box for bias grads
+  static constexpr int kBarOff = kOnesOff + 8192;
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 1) * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kAlloc = kTotal + 1024;
@@ -369,14 +371,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == kEpiWarp0) tmem_alloc<256>(tmem_ptr);
+  if (warp == kEpiWarp0) tmem_alloc<512>(tmem_ptr);
+  {  // bf16 1.0 everywhere: as an MN-major B operand it makes column 256.. of the accumulator the column sums of dY
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + L::kOnesOff);
+    for (int i = threadIdx.x; i < 8192 / 4; i += kThreads) ones[i] = 0x3F803F80u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const bool want_db = args.db != nullptr;
   if (num_kb == 0) {  // nothing to contribute (uniform across the CTA)
     __syncthreads();
-    if (warp == kEpiWarp0) tmem_dealloc<256>(tmem_base);
+    if (warp == kEpiWarp0) tmem_dealloc<512>(tmem_base);
     return;
   }
 
@@ -400,6 +408,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      const uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 1);
+      const uint64_t odesc = make_smem_desc(smem_u32(smem + L::kOnesOff), 8192, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -414,6 +424,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         for (int k = 0; k < 4; ++k) {
           // 16 points = 16 rows of 128 B = 2048 B -> +128 in the (addr >> 4) field
           umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+          if (want_db) umma_bf16(tmem_base + 256, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
         }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -436,10 +447,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
           if (c0 + j < args.n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
       }
     }
+    if (want_db) {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + 256 + ((uint32_t)(q * 32) << 16), r);
+      tmem_ld_wait();
+      if (m < args.M) atomicAdd(args.db + m, __uint_as_float(r[0]));
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarp0) tmem_dealloc<256>(tmem_base);
+  if (warp == kEpiWarp0) tmem_dealloc<512>(tmem_base);
 }
 
 // column sums of a bf16 matrix (bias gradients): out[n] += sum_p Y[p, col0 + n]
@@ -552,6 +569,7 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   WgradArgs a;
   a.dy_col = g.dy_col; a.x_col = g.x_col; a.P = (int)g.P; a.M = g.M; a.N = g.N; a.dW = g.dW; a.ldw = g.ldw; a.w_col = g.w_col;
   a.n_valid = g.n_valid > 0 ? g.n_valid : g.N;
+  a.db = g.db;
   int m_tiles = (g.M + 127) / 128;
   int total_kb = (int)((g.P + 63) / 64);
   int splits = kNumSMs / m_tiles;
@@ -612,12 +630,12 @@ extern "C" int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, v
   return nmx::launch_gemm(g, (cudaStream_t)stream);
 }
 
-extern "C" int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, int64_t P, int M, int N, void* stream) {
+extern "C" int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, float* db, int64_t P, int M, int N, void* stream) {
   NMX_CHECK_ARG(dY && X && dW && P >= 0, "dY, X, dW non-null; P >= 0");
   nmx::WgradDesc g{};
   g.dY = dY; g.dy_cols = M; g.dy_ld = M; g.dy_col = 0;
   g.X = X; g.x_cols = N; g.x_ld = N; g.x_col = 0;
-  g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = N; g.w_col = 0; g.n_valid = N;
+  g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = N; g.w_col = 0; g.n_valid = N; g.db = db;
   return nmx::launch_wgrad(g, (cudaStream_t)stream);
 }
 

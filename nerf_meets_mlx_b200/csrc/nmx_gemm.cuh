@@ -23,6 +23,7 @@ struct WgradDesc {
   const void* X; int x_cols, x_ld, x_col;
   int64_t P; int M, N;                                // M % 64 == 0, N % 64 == 0 (<= 256)
   float* dW; int ldw, w_col; int n_valid;             // only columns < n_valid are accumulated
+  float* db;                                          // optional: db[m] += sum_p dY[p, m] (bias gradient), or null
 };
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);

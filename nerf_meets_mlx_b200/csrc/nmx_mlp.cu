@@ -231,12 +231,21 @@ head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
-    for (int k0 = lane * 2; k0 < K; k0 += 64) {
-      __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(h + p * ldh + k0);
-      float h0 = __bfloat162float(hv.x), h1 = __bfloat162float(hv.y);
+    for (int k0 = lane * 8; k0 < K; k0 += 256) {  // one 16 B vector load per lane: a coalesced 2*K-byte row
+      uint4 raw = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + k0));
+      const bf16* hv = reinterpret_cast<const bf16*>(&raw);
+      float hf[8];
 #pragma unroll
-      for (int o = 0; o < 8; ++o)
-        if (o < n_out) acc[o] += h0 * s_w[o * K + k0] + h1 * s_w[o * K + k0 + 1];
+      for (int e = 0; e < 8; ++e) hf[e] = __bfloat162float(hv[e]);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        if (o < n_out) {
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + o * K + k0);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_w + o * K + k0 + 4);
+          acc[o] += hf[0] * w0.x + hf[1] * w0.y + hf[2] * w0.z + hf[3] * w0.w + hf[4] * w1.x + hf[5] * w1.y +
+                    hf[6] * w1.z + hf[7] * w1.w;
+        }
+      }
     }
 #pragma unroll
     for (int o = 0; o < 8; ++o)
@@ -254,43 +263,102 @@ head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
 // backward of a small head: d_out[p, col0 + o] given.
 //   dW[o, k] += sum_p d_out[p,o] h[p,k] ; db[o] += sum_p d_out[p,o]
 //   optionally d_h[p, k] = (sum_o d_out[p,o] W[o,k]) * (h[p,k] > 0)   (bf16; when the head input is post-ReLU)
-// Block = K threads (thread k owns column k), grid-strided over slabs of points.
+// One warp per point per iteration: lane l owns CPL = K/32 adjacent columns (one 4/8/16 B vector load of the bf16 row,
+// a coalesced 2*K-byte warp transaction), keeps its dW partials in registers over the whole point loop, and the block
+// reduces them through shared memory into ONE set of atomics.
+template <int CPL, int NOUT>
 __global__ void __launch_bounds__(256)
-head_bwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restrict__ Wt, int n_out,
-                const float* __restrict__ d_out, int ldo, int col0, int64_t P, float* __restrict__ dW,
-                float* __restrict__ db, bf16* __restrict__ d_h, int ldd) {
-  const int k = threadIdx.x;
-  float w[8], acc[8], accb[8];
+head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ Wt, const float* __restrict__ d_out,
+                int ldo, int col0, int64_t P, float* __restrict__ dW, float* __restrict__ db, bf16* __restrict__ d_h,
+                int ldd) {
+  constexpr int K = CPL * 32;
+  __shared__ float s_acc[NOUT * K + NOUT];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < NOUT * K + NOUT; i += blockDim.x) s_acc[i] = 0.0f;
+  __syncthreads();
+  float w[NOUT][CPL], acc[NOUT][CPL], accb[NOUT];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    w[o] = (o < n_out && k < K) ? Wt[o * K + k] : 0.0f;
-    acc[o] = 0.0f;
+  for (int o = 0; o < NOUT; ++o) {
     accb[o] = 0.0f;
-  }
-  if (k < K) {
-#pragma unroll 4
-    for (int64_t p = blockIdx.x; p < P; p += gridDim.x) {
-      float hv = __bfloat162float(h[p * ldh + k]);
-      float dh = 0.0f;
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        if (o < n_out) {
-          float d = __ldg(d_out + p * ldo + col0 + o);
-          acc[o] += d * hv;
-          if (k == 0) accb[o] += d;
-          dh += d * w[o];
-        }
-      }
-      if (d_h != nullptr) d_h[p * ldd + k] = __float2bfloat16_rn(hv > 0.0f ? dh : 0.0f);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      if (o < n_out) {
-        atomicAdd(dW + o * K + k, acc[o]);
-        if (k == 0) atomicAdd(db + o, accb[o]);
-      }
+    for (int c = 0; c < CPL; ++c) {
+      w[o][c] = Wt[o * K + lane * CPL + c];
+      acc[o][c] = 0.0f;
     }
   }
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;
+  const int64_t gstride = (int64_t)gridDim.x * nwarps;
+#pragma unroll 2
+  for (int64_t p = gw; p < P; p += gstride) {
+    bf16 hv[CPL];
+    if constexpr (CPL == 8) *reinterpret_cast<uint4*>(hv) = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + lane * CPL));
+    else if constexpr (CPL == 4) *reinterpret_cast<uint2*>(hv) = __ldg(reinterpret_cast<const uint2*>(h + p * ldh + lane * CPL));
+    else *reinterpret_cast<uint32_t*>(hv) = __ldg(reinterpret_cast<const uint32_t*>(h + p * ldh + lane * CPL));
+    float d[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) d[o] = __ldg(d_out + p * ldo + col0 + o);
+    float dh[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      float x = __bfloat162float(hv[c]);
+      float t = 0.0f;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) {
+        acc[o][c] += d[o] * x;
+        t += d[o] * w[o][c];
+      }
+      dh[c] = x > 0.0f ? t : 0.0f;
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) accb[o] += d[o];
+    if (d_h != nullptr) {
+      bf16 ov[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) ov[c] = __float2bfloat16_rn(dh[c]);
+      if constexpr (CPL == 8) *reinterpret_cast<uint4*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint4*>(ov);
+      else if constexpr (CPL == 4) *reinterpret_cast<uint2*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint2*>(ov);
+      else *reinterpret_cast<uint32_t*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint32_t*>(ov);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) atomicAdd(&s_acc[o * K + lane * CPL + c], acc[o][c]);
+    if (lane == 0) atomicAdd(&s_acc[NOUT * K + o], accb[o]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) atomicAdd(dW + i, s_acc[i]);
+  if (threadIdx.x < NOUT) atomicAdd(db + threadIdx.x, s_acc[NOUT * K + threadIdx.x]);
+}
+
+template <int CPL>
+int launch_head_bwd_nout(int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
+                         int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
+  const int blocks = kNumSMs * 2;
+#define NMX_HB(NO)                                                                                               \
+  case NO:                                                                                                       \
+    head_bwd_kernel<CPL, NO><<<blocks, 256, 0, s>>>(h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd);          \
+    break;
+  switch (n_out) {
+    NMX_HB(1) NMX_HB(2) NMX_HB(3) NMX_HB(4) NMX_HB(5) NMX_HB(6) NMX_HB(7) NMX_HB(8)
+    default:
+      set_error("head_bwd: n_out must be in [1,8]");
+      return NMX_E_BADARG;
+  }
+#undef NMX_HB
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_head_bwd(int K, int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
+                    int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
+  if (K == 256) return launch_head_bwd_nout<8>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  if (K == 128) return launch_head_bwd_nout<4>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  if (K == 64) return launch_head_bwd_nout<2>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  set_error("head_bwd: K must be 64, 128 or 256 (got %d)", K);
+  return NMX_E_UNSUPPORTED;
 }
 
 }  // namespace
@@ -317,7 +385,7 @@ extern "C" int64_t nmx_mlp_param_count(const nmx_mlp_config* c) {
 extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, nmx_mlp_plan** out) {
   NMX_CHECK_ARG(c && out && max_points > 0, "cfg, out non-null; max_points > 0");
   NMX_CHECK_ARG(c->n_layers >= 1 && c->n_layers <= 12, "1 <= n_layers <= 12");
-  NMX_CHECK_ARG(c->width % 64 == 0 && c->width >= 64 && c->width <= 256, "width must be 64, 128, 192 or 256");
+  NMX_CHECK_ARG(c->width == 64 || c->width == 128 || c->width == 256, "width must be 64, 128 or 256");
   NMX_CHECK_ARG(!c->use_viewdirs || c->width % 128 == 0, "view-dir head needs width 128 or 256");
   NMX_CHECK_ARG(c->in_pos >= 1 && c->in_pos <= 256, "1 <= in_pos <= 256");
   NMX_CHECK_ARG(c->in_dir >= 0 && c->in_dir <= 64, "0 <= in_dir <= 64");
@@ -587,14 +655,13 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
   int rc;
   int cur = 0;  // index of the gradient buffer holding dY of the layer being processed
   const bf16* hl = c.H(p->D - 1);
-  const int hb_blocks = kNumSMs * 4;
 
   auto wgrad = [&](const bf16* dY, int dy_cols, const bf16* X, int x_cols, int x_col, int M, int N, int n_valid,
-                   float* dW, int ldw, int w_col) {
+                   float* dW, int ldw, int w_col, float* db) {
     WgradDesc g{};
     g.dY = dY; g.dy_cols = dy_cols; g.dy_ld = dy_cols; g.dy_col = 0;
     g.X = X; g.x_cols = x_cols; g.x_ld = x_cols; g.x_col = x_col;
-    g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid;
+    g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid; g.db = db;
     return launch_wgrad(g, s);
   };
 
@@ -606,27 +673,22 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
   }
   if (p->cfg.use_viewdirs) {
     // rgb head: d_hd_pre = (d_rgb W_rgb) * [hd > 0]; dW_rgb, db_rgb
-    head_bwd_kernel<<<hb_blocks, W / 2 < 32 ? 32 : W / 2, 0, s>>>(c.HD(), W / 2, W / 2, params + p->rgb.w_off, 3, d_out,
-                                                                  out_cols, 0, P, d_params + p->rgb.w_off,
-                                                                  d_params + p->rgb.b_off, c.GHD(), W / 2);
-    NMX_LAUNCH_CHECK();
+    if ((rc = launch_head_bwd(W / 2, 3, c.HD(), W / 2, params + p->rgb.w_off, d_out, out_cols, 0, P,
+                              d_params + p->rgb.w_off, d_params + p->rgb.b_off, c.GHD(), W / 2, s))) return rc;
     // alpha head: dW_alpha, db_alpha (its d_h is the rank-1 term of the feature dgrad epilogue)
-    head_bwd_kernel<<<hb_blocks, W, 0, s>>>(hl, W, W, params + p->alpha.w_off, 1, d_out, out_cols, 3, P,
-                                            d_params + p->alpha.w_off, d_params + p->alpha.b_off, nullptr, 0);
-    NMX_LAUNCH_CHECK();
+    if ((rc = launch_head_bwd(W, 1, hl, W, params + p->alpha.w_off, d_out, out_cols, 3, P, d_params + p->alpha.w_off,
+                              d_params + p->alpha.b_off, nullptr, 0, s))) return rc;
     // dir layer: wgrad over [feature | dir PE], bias, dgrad to feature
     float* dWd = d_params + p->dir.w_off;
-    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0))) return rc;
-    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W))) return rc;
-    if ((rc = launch_colsum(c.GHD(), W / 2, 0, W / 2, P, d_params + p->dir.b_off, s))) return rc;
+    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
+    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
     GemmDesc g{};
     g.A0 = c.GHD(); g.a0_rows = P; g.a0_cols = W / 2; g.a0_ld = W / 2; g.a0_k = W / 2;
     g.B = c.ws + p->wt_dir; g.b_rows = W; g.b_cols = W / 2; g.b_ld = W / 2;
     g.M = P; g.N = W; g.D = c.G(0); g.ldd = W;
     if ((rc = launch_gemm(g, s))) return rc;
     // feature layer: wgrad, bias, dgrad (+ alpha rank-1 term, ReLU mask of h_{D-1})
-    if ((rc = wgrad(c.G(0), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0))) return rc;
-    if ((rc = launch_colsum(c.G(0), W, 0, W, P, d_params + p->feat.b_off, s))) return rc;
+    if ((rc = wgrad(c.G(0), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
     GemmDesc f{};
     f.A0 = c.G(0); f.a0_rows = P; f.a0_cols = W; f.a0_ld = W; f.a0_k = W;
     f.B = c.ws + p->wt_feat; f.b_rows = W; f.b_cols = W; f.b_ld = W;
@@ -636,9 +698,8 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
     cur = 1;
   } else {
     // no-view head: d_h = (d_out W_out) * [h > 0]; dW_out, db_out
-    head_bwd_kernel<<<hb_blocks, W, 0, s>>>(hl, W, W, params + p->outl.w_off, p->cfg.out_ch, d_out, out_cols, 0, P,
-                                            d_params + p->outl.w_off, d_params + p->outl.b_off, c.G(0), W);
-    NMX_LAUNCH_CHECK();
+    if ((rc = launch_head_bwd(W, p->cfg.out_ch, hl, W, params + p->outl.w_off, d_out, out_cols, 0, P,
+                              d_params + p->outl.w_off, d_params + p->outl.b_off, c.G(0), W, s))) return rc;
     cur = 0;
   }
   for (int l = p->D - 1; l >= 0; --l) {
@@ -646,15 +707,15 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
     const bf16* dY = c.G(cur);
     float* dW = d_params + r.w_off;
     bool skip_in = (r.in == W + p->in_pos);
+    float* db = d_params + r.b_off;
     if (l == 0) {
-      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0))) return rc;
+      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
     } else if (skip_in) {
-      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0))) return rc;
-      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos))) return rc;
+      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
+      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
     } else {
-      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0))) return rc;
+      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
     }
-    if ((rc = launch_colsum(dY, W, 0, W, P, d_params + r.b_off, s))) return rc;
     if (l >= 1) {
       GemmDesc g{};
       g.A0 = dY; g.a0_rows = P; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;

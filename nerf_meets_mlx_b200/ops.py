@@ -183,14 +183,16 @@ def gemm_bf16(A, B, bias=None, relu=False, out_fp32=False):
     return D
 
 
-def wgrad_bf16(dY, X):
-    """dW[M,N] = dY[P,M].T @ X[P,N] in fp32 (tcgen05 kernel, MN-major operands; unit-test hook)."""
+def wgrad_bf16(dY, X, want_db=False):
+    """dW[M,N] = dY[P,M].T @ X[P,N] in fp32 (tcgen05 kernel, MN-major operands; unit-test hook).
+    want_db: also return db[M] = column sums of dY (bias gradient) from the fused ones-column MMA."""
     require_cuda(dY, X)
     P, M = dY.shape
     N = X.shape[1]
     dW = torch.zeros((M, N), dtype=torch.float32, device=dY.device)
-    call("nmx_wgrad_bf16", ptr(dY), ptr(X), ptr(dW), i64(P), i32(M), i32(N), stream())
-    return dW
+    db = torch.zeros((M,), dtype=torch.float32, device=dY.device) if want_db else None
+    call("nmx_wgrad_bf16", ptr(dY), ptr(X), ptr(dW), ptr(db), i64(P), i32(M), i32(N), stream())
+    return (dW, db) if want_db else dW
 
 
 def colsum_bf16(Y):

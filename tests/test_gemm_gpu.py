@@ -35,10 +35,14 @@ def test_wgrad_mnmajor(ops, P, M, N):
     dY = (torch.randn(P, M, device="cuda") * 0.2).bfloat16()
     X = (torch.randn(P, N, device="cuda") * 0.5).bfloat16()
     ref = dY.float().T @ X.float()
-    out = ops.wgrad_bf16(dY, X)
+    out, db = ops.wgrad_bf16(dY, X, want_db=True)
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3 * scale), ((out - ref).abs().max().item(), scale)
+    ref_b = dY.float().sum(0)
+    assert torch.allclose(db, ref_b, rtol=1e-3, atol=1e-3 * ref_b.abs().max().item()), (db - ref_b).abs().max().item()
+    out2 = ops.wgrad_bf16(dY, X)
+    assert torch.equal(out2 != 0, out != 0)
 
 
 def test_colsum(ops):
