@@ -1,0 +1,46 @@
+// Host/device description of the fused MLP forward chain (nmx_chain.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nmx {
+
+constexpr int kMaxChainLayers = 10;
+constexpr int kSrcPos = 4;  // A slab = encoded-position chunk of the input tile
+constexpr int kSrcDir = 5;  // A slab = encoded-view-dir chunk of the input tile (0..3 = activation chunk index)
+
+struct ChainLayerDesc {
+  int n_slabs;     // K / 64
+  int src[5];      // A-operand source of every K slab
+  int N;           // 256 or 128
+  int relu;
+  int bias_off;    // float offset into params
+  int feeds_next;  // its output chunks are the A operand of a later layer (MMA waits on act_ready)
+  int save_kind;   // 0 none, 1 = [rows, 256] activation store (h_l / feature), 2 = [P, 128] store (hd)
+  int save_row0;   // first row of this layer's region in the activation store
+};
+
+struct ChainParams {
+  int n_layers;
+  ChainLayerDesc L[kMaxChainLayers];
+  int P, save;
+  const float* params;
+  float* out;
+  int out_cols;
+  int head7_layer, head7_n, head7_w_off, head7_b_off;  // alpha (n=1) or output_linear (n=out_ch) from h_{D-1}
+  int rgb_layer, rgb_w_off, rgb_b_off;                 // rgb head from the dir layer's output, or rgb_layer = -1
+  int uses_dir, x0_dir_col;
+  int pos_last_layer, pos_prefetch_layer, dir_layer;
+};
+
+struct ChainMaps {
+  CUtensorMap w[kMaxChainLayers];  // bf16 weights [N_l, K_l] (padded K), box 64 x 128
+  CUtensorMap x0;                  // encoded input [P, pos_pad + dir_pad], box 64 x 128
+  CUtensorMap save;                // activation store [(D+1) * cap, 256], box 64 x 128
+  CUtensorMap hd;                  // [P, 128], box 64 x 128
+};
+
+int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream);
+
+}  // namespace nmx

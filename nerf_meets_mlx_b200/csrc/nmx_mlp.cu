@@ -9,10 +9,13 @@
 //             MN-major operands straight from the saved row-major activations) + a column-sum for the bias.
 // Dead work skipped exactly as autograd would: no dgrad into pure-encoding inputs.
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "nmx_common.cuh"
 #include "nmx_gemm.cuh"
+#include "nmx_chain.cuh"
+#include "nmx_sm100.cuh"
 
 
 using namespace nmx;
@@ -48,6 +51,10 @@ struct nmx_mlp_plan {
 
 namespace {
 
+bool chain_eligible(const nmx_mlp_plan* p);
+// points per inference chunk: the fused chain only needs the encoded-input tile per chunk -> 16 full waves of tiles
+int64_t infer_cap(const nmx_mlp_plan* p) { return chain_eligible(p) ? (int64_t)kNumSMs * 128 * 16 : kInferChunk; }
+
 struct ActLayout {
   int64_t x0, h0, feat, hd, g0, g1, ghd, dsig, total;
   int64_t h_stride;  // bytes between consecutive saved trunk activations (0 = ping-pong of 2 buffers)
@@ -57,12 +64,13 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   ActLayout a;
   int64_t off = 0;
   a.x0 = off; off += align256(cap * p->x0_cols * 2);
-  int64_t hbytes = align256(cap * p->W * 2);
+  const bool x0_only = !training && chain_eligible(p);  // inference through the fused chain keeps activations on chip
+  int64_t hbytes = x0_only ? 0 : align256(cap * p->W * 2);
   a.h0 = off;
   a.h_stride = hbytes;
   off += hbytes * (training ? p->D : 2);
   a.feat = off; off += hbytes;
-  a.hd = off; off += align256(cap * (p->W / 2) * 2);
+  a.hd = off; off += x0_only ? 0 : align256(cap * (p->W / 2) * 2);
   a.g0 = a.g1 = a.ghd = a.dsig = 0;
   if (training) {
     a.g0 = off; off += hbytes;
@@ -394,7 +402,7 @@ extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, 
   NMX_CHECK_ARG(c->skip_layer < c->n_layers - 1, "skip_layer must be < n_layers - 1 (or -1)");
   nmx_mlp_plan* p = new nmx_mlp_plan();
   p->cfg = *c;
-  p->max_points = max_points;
+  p->max_points = (max_points + 127) / 128 * 128;  // activation regions hold whole 128-point tiles
   p->D = c->n_layers;
   p->W = c->width;
   p->in_pos = c->in_pos;
@@ -447,16 +455,16 @@ extern "C" void nmx_mlp_plan_destroy(nmx_mlp_plan* plan) { delete plan; }
 namespace {
 // per-ray view-dir PE scratch: one row per ray of the current pass / inference chunk (rays <= points)
 int64_t dirpe_bytes(const nmx_mlp_plan* p) {
-  int64_t rows = p->max_points > kInferChunk ? p->max_points : kInferChunk;
+  int64_t rows = p->max_points > infer_cap(p) ? p->max_points : infer_cap(p);
   return align256(rows * (int64_t)(p->dir_pad > 0 ? p->dir_pad : 1) * 2);
 }
 }
 
 extern "C" int64_t nmx_mlp_workspace_bytes(const nmx_mlp_plan* p, int training) {
   if (!p) return -1;
-  int64_t cap = training ? p->max_points : kInferChunk;
+  int64_t cap = training ? p->max_points : infer_cap(p);
   if (training) {  // a training workspace also serves inference passes (chunked layout must fit)
-    int64_t ti = act_layout(p, kInferChunk, false).total, tt = act_layout(p, cap, true).total;
+    int64_t ti = act_layout(p, infer_cap(p), false).total, tt = act_layout(p, cap, true).total;
     return p->weights_bytes + dirpe_bytes(p) + (ti > tt ? ti : tt) + 1024;
   }
   return p->weights_bytes + dirpe_bytes(p) + act_layout(p, cap, training != 0).total + 1024;
@@ -603,6 +611,91 @@ int forward_chunk(const Ctx& c, int64_t npts, float* out, int out_cols) {
 
 }  // namespace
 
+// ---- fused chain (nmx_chain.cu): whole MLP per 128-point tile, activations stay on chip
+namespace {
+bool chain_eligible(const nmx_mlp_plan* p) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("NMX_DISABLE_CHAIN");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (disabled) return false;
+  const int layers = p->D + (p->cfg.use_viewdirs ? 2 : 0);
+  return p->W == 256 && p->pos_pad == 64 && (p->dir_pad == 0 || p->dir_pad == 64) && layers <= kMaxChainLayers &&
+         p->D >= 2;
+}
+
+int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_cols) {
+  nmx_mlp_plan* p = c.p;
+  const int W = p->W, D = p->D;
+  ChainMaps maps;
+  ChainParams prm;
+  memset(&prm, 0, sizeof(prm));
+  int rc;
+  int nl = 0;
+  prm.pos_last_layer = 0;
+  prm.dir_layer = -1;
+  for (int l = 0; l < D; ++l, ++nl) {
+    ChainLayerDesc& d = prm.L[nl];
+    const bool skip_in = (p->trunk[l].in == W + p->in_pos);
+    int ns = 0;
+    if (l == 0) {
+      d.src[ns++] = kSrcPos;
+    } else {
+      if (skip_in) { d.src[ns++] = kSrcPos; prm.pos_last_layer = nl; }
+      for (int k = 0; k < 4; ++k) d.src[ns++] = k;
+    }
+    d.n_slabs = ns; d.N = W; d.relu = 1; d.bias_off = (int)p->trunk[l].b_off;
+    d.feeds_next = (l < D - 1) || p->cfg.use_viewdirs;
+    d.save_kind = c.training ? 1 : 0; d.save_row0 = (int)(l * cap);
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_off[l], W, p->wf_k[l], p->wf_k[l], 128))) return rc;
+  }
+  prm.head7_layer = D - 1;
+  prm.rgb_layer = -1;
+  if (p->cfg.use_viewdirs) {
+    ChainLayerDesc& f = prm.L[nl];
+    for (int k = 0; k < 4; ++k) f.src[k] = k;
+    f.n_slabs = 4; f.N = W; f.relu = 0; f.bias_off = (int)p->feat.b_off; f.feeds_next = 1;
+    f.save_kind = c.training ? 1 : 0; f.save_row0 = (int)(D * cap);
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_feat, W, W, W, 128))) return rc;
+    ++nl;
+    ChainLayerDesc& d = prm.L[nl];
+    for (int k = 0; k < 4; ++k) d.src[k] = k;
+    d.src[4] = kSrcDir;
+    d.n_slabs = 5; d.N = W / 2; d.relu = 1; d.bias_off = (int)p->dir.b_off; d.feeds_next = 0;
+    d.save_kind = c.training ? 2 : 0; d.save_row0 = 0;
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_dir, W / 2, p->wf_dir_k, p->wf_dir_k, 128))) return rc;
+    prm.dir_layer = nl;
+    prm.rgb_layer = nl;
+    ++nl;
+    prm.head7_n = 1; prm.head7_w_off = (int)p->alpha.w_off; prm.head7_b_off = (int)p->alpha.b_off;
+    prm.rgb_w_off = (int)p->rgb.w_off; prm.rgb_b_off = (int)p->rgb.b_off;
+    prm.uses_dir = 1; prm.x0_dir_col = p->pos_pad;
+  } else {
+    prm.head7_n = p->cfg.out_ch; prm.head7_w_off = (int)p->outl.w_off; prm.head7_b_off = (int)p->outl.b_off;
+    prm.uses_dir = 0;
+  }
+  for (int l = nl; l < kMaxChainLayers; ++l) maps.w[l] = maps.w[0];
+  prm.n_layers = nl;
+  prm.pos_prefetch_layer = prm.pos_last_layer + 2 < nl ? prm.pos_last_layer + 2 : nl - 1;
+  prm.P = (int)npts; prm.save = c.training ? 1 : 0; prm.params = c.params; prm.out = out; prm.out_cols = out_cols;
+  if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
+  if (c.training) {
+    if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
+    if (p->cfg.use_viewdirs) {
+      if ((rc = make_tmap_bf16_2d(&maps.hd, c.HD(), npts, W / 2, W / 2, 128))) return rc;
+    } else {
+      maps.hd = maps.x0;
+    }
+  } else {
+    maps.save = maps.x0;
+    maps.hd = maps.x0;
+  }
+  return launch_chain_fwd(maps, prm, c.s);
+}
+
+}  // namespace
+
 extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
                            const float* x_or_rays, int ray_stride, const float* z, const float* bands, float* out,
                            int64_t B, int n, int save_activations, void* stream_) {
@@ -626,14 +719,17 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   if (c.training) {
     c.al = act_layout(p, p->max_points, true);
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
+    if (chain_eligible(p)) return forward_chain(c, P, p->max_points, out, out_cols);
     return forward_chunk(c, P, out, out_cols);
   }
-  int64_t cap = kInferChunk;
+  int64_t cap = infer_cap(p);
   c.al = act_layout(p, cap, false);
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t npts = P - p0 < cap ? P - p0 : cap;
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
-    if ((rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols))) return rc;
+    if (chain_eligible(p)) rc = forward_chain(c, npts, cap, out + p0 * out_cols, out_cols);
+    else rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols);
+    if (rc) return rc;
   }
   return 0;
 }
