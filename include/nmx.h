@@ -157,6 +157,14 @@ int nmx_colsum_bf16(const void* Y, float* out, int64_t P, int N, void* stream);
 int nmx_profile_enable(int on);
 int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t* launches);
 
+/* ---- diagnostics (not on the product path; used by scripts/ to calibrate the roofline) ------------------------
+ * nmx_diag_mma_rate: every CTA issues `iters` back-to-back M=128 x N x K=16 bf16 tcgen05 MMAs on resident operands;
+ * out[2*cta] = SM clocks, out[2*cta+1] = nanoseconds.
+ * nmx_chain_trace_read: copies the (clock, ns) event trace the fused MLP chain records for CTA 0 when the environment
+ * variable NMX_CHAIN_DBG has bit 2 set. */
+int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream);
+int nmx_chain_trace_read(long long* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

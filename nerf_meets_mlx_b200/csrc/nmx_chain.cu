@@ -1,16 +1,17 @@
 // K3 fused forward chain: the whole NeRF MLP (models/NeRF.py:201-243) for a 128-point tile in ONE persistent kernel.
 //
 // Activations never leave the SM between layers: the epilogue of layer l writes relu(acc + b) as bf16 straight into
-// the 128B-swizzled shared-memory tile that is the A operand of layer l+1 (in place, chunk by chunk, so the MMAs of
-// layer l+1 start as soon as the first 64-column chunk exists), accumulators ping-pong between the two halves of
-// TMEM, and the weights (2.4 MB bf16 per net, L2-resident) stream through a TMA ring in 64-wide K slabs.  The skip
-// concat [input_pos, h] and the view-dir concat [feature, input_dir] are extra K slabs read from the resident
-// encoded-input tile.  The N=1 / N=3 / N<=8 heads (alpha, rgb, output_linear) are evaluated by the epilogue threads
-// from the values they already hold in registers.  When training, each finished chunk is also TMA-stored to the
-// saved-activation buffers (the smem tile doubles as the staging buffer).
+// the 128B-swizzled shared-memory tile that is the A operand of layer l+1 (in place, 64-column chunk by chunk, all
+// eight epilogue warps on the same chunk so the MMAs of layer l+1 start as soon as chunk 0 exists), accumulators
+// ping-pong between the two halves of TMEM, and the weights (2.4 MB bf16 per net, L2-resident) stream through a TMA
+// ring in 64-wide K slabs.  The skip concat [input_pos, h] and the view-dir concat [feature, input_dir] are extra K
+// slabs read from the resident encoded-input tile.  The N=1 / N=3 / N<=8 heads (alpha, rgb, output_linear) are
+// evaluated by the epilogue threads from the values they already hold in registers.  When training, a dedicated
+// warp TMA-stores each finished chunk to the saved-activation buffers (the smem tile doubles as the staging buffer).
 //
-// Roles (320 threads): warp 0 = TMA producer (weight ring + encoded-input tile), warp 1 = MMA issuer (one lane),
-// warps 2..9 = epilogue, two warps per TMEM lane quadrant; epilogue group g = (warp-2)/4 owns columns [128g, 128g+128).
+// Roles (640 threads): warp 0 = TMA producer (weight ring + encoded-input tile), warp 1 = MMA issuer,
+// warp 2 = activation-store issuer (training only), warps 4..19 = epilogue (four warps per TMEM lane quadrant, each
+// taking 16 of a chunk's 64 columns).
 // Roofline: tensor pipe (inference: ~0 HBM traffic; training: 512 B/point/layer of activation stores).
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
@@ -21,7 +22,10 @@ using namespace nmx::sm100;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kEpiWarps = 16;               // 4 per TMEM lane quadrant
+constexpr int kEpiCols = 64 / (kEpiWarps / 4);  // columns of a 64-column chunk one epilogue warp handles (16 or 32)
+constexpr int kEpiWarp0 = 4;                // warps 0 TMA, 1 MMA, 2 activation store + TMEM alloc, 3 idle, 4.. epilogue
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kStages = 3;
 constexpr int kSlabBytes = 256 * 64 * 2;   // one 64-wide K slab of a 256-row weight matrix
 constexpr int kChunkBytes = 128 * 64 * 2;  // one 128-row x 64-col bf16 activation chunk
@@ -33,25 +37,157 @@ struct Smem {
   static constexpr int kBiasOff = kRingOff + kStages * kSlabBytes;       // [kMaxChainLayers][256] fp32
   static constexpr int kW7Off = kBiasOff + kMaxChainLayers * 256 * 4;    // head-7 weights [8][256] fp32
   static constexpr int kWrgbOff = kW7Off + 8 * 256 * 4;                  // rgb weights [3][128] fp32
-  static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                // [128][12] fp32 partial sums
-  static constexpr int kBarOff = kXchgOff + 128 * 12 * 4;
-  // barriers: full[S], empty[S], tfull[2], tempty[2], act_ready[4], x0pos_full, x0pos_empty, x0dir_full, x0dir_empty
-  static constexpr int kNumBars = 2 * kStages + 2 + 2 + 4 + 4;
+  static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                // [3][128][4] fp32 partial sums
+  static constexpr int kBarOff = kXchgOff + 3 * 128 * 4 * 4;
+  // barriers: full[S], empty[S], tfull[2], tempty[2], act_ready[4], x0pos_full, x0pos_empty, x0dir_full, x0dir_empty,
+  //           store_done
+  static constexpr int kNumBars = 2 * kStages + 2 + 2 + 4 + 4 + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kAlloc = kTotal + 1024;
 };
 
+// NMX_CHAIN_DBG bit 2: CTA 0 records (clock64, globaltimer) at pipeline events of its first kTraceTiles tiles
+constexpr int kTraceTiles = 6;
+__device__ long long g_trace[2][kTraceTiles][kMaxChainLayers][4][2];
+__device__ __forceinline__ void trace(bool on, int role, int it, int l, int ev) {
+  if (on && it < kTraceTiles) {
+    long long c = clock64();
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    g_trace[role][it][l][ev][0] = c;
+    g_trace[role][it][l][ev][1] = (long long)g;
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float round_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// read-only staging data (biases / head weights written once before the first __syncthreads): schedulable loads
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int C>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  if constexpr (C == 32) tmem_ld_32x32(taddr, r);
+  else tmem_ld_32x16(taddr, r);
+}
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above it
+template <int C>
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
+  if constexpr (C == 16) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+  }
+}
+
+// Epilogue of one layer for one warp: for every 64-column chunk, this warp's kEpiCols columns x 32 rows:
+// TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand of the next layer / TMA-store source),
+// optional register heads.  HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
+// The TMEM load of chunk c+1 is issued before the math of chunk c (two register sets).
+// math + store of one chunk's columns held in r[] (fp32 accumulators of this thread's row)
+template <bool RELU, int HEAD>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[kEpiCols], const int c, const int c0, const int part,
+                                          const uint32_t bias_addr, const uint32_t act_row_addr, const uint32_t swz,
+                                          const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3]) {
+  constexpr int C = kEpiCols;
+  float4 b[C / 4];
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) b[i] = lds128(bias_addr + (uint32_t)(c0 + i * 4) * 4u);
+  const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
+#pragma unroll
+  for (int p4 = 0; p4 < C / 8; ++p4) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float4 bb = b[p4 * 2 + (e >> 2)];
+      const float be = (e & 3) == 0 ? bb.x : (e & 3) == 1 ? bb.y : (e & 3) == 2 ? bb.z : bb.w;
+      const float x = __uint_as_float(r[p4 * 8 + e]) + be;
+      v[e] = RELU ? fmaxf(x, 0.0f) : x;
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
+    sts128(so + ((((uint32_t)(part * (C / 8) + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+    if (HEAD != 0) {
+      float xr[8];  // the bf16-rounded activations (what a separate head kernel would read back)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xr[2 * e] = __uint_as_float(pk[e] << 16);
+        xr[2 * e + 1] = __uint_as_float(pk[e] & 0xffff0000u);
+      }
+      const int col = c0 + p4 * 8;
+      if (HEAD == 1 || HEAD == 3) {  // 1: single output (alpha); 3: up to 8 outputs (output_linear)
+#pragma unroll
+        for (int o = 0; o < (HEAD == 1 ? 1 : 8); ++o) {
+          if (HEAD == 1 || o < head_n) {
+            const float4 w0 = lds128(hw_addr + (uint32_t)(o * 256 + col) * 4u);
+            const float4 w1 = lds128(hw_addr + (uint32_t)(o * 256 + col + 4) * 4u);
+            hp[o] += xr[0] * w0.x + xr[1] * w0.y + xr[2] * w0.z + xr[3] * w0.w + xr[4] * w1.x + xr[5] * w1.y +
+                     xr[6] * w1.z + xr[7] * w1.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float4 w0 = lds128(hw_addr + (uint32_t)(o * 128 + col) * 4u);
+          const float4 w1 = lds128(hw_addr + (uint32_t)(o * 128 + col + 4) * 4u);
+          rgbp[o] += xr[0] * w0.x + xr[1] * w0.y + xr[2] * w0.z + xr[3] * w0.w + xr[4] * w1.x + xr[5] * w1.y +
+                     xr[6] * w1.z + xr[7] * w1.w;
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();
+}
+
+// Epilogue of one layer for one warp: for every 64-column chunk, this warp's kEpiCols columns x 32 rows:
+// TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand of the next layer / TMA-store source),
+// optional register heads.  HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
+template <bool RELU, int HEAD>
+__device__ __forceinline__ void epi_layer(const uint32_t tacc, const int nck, const int part, const uint32_t bias_addr,
+                                          const uint32_t act_row_addr, const uint32_t swz, uint64_t* act_ready,
+                                          const bool signal, const int lane, const uint32_t hw_addr, const int head_n,
+                                          float (&hp)[8], float (&rgbp)[3], const bool skip_math) {
+  constexpr int C = kEpiCols;  // 16 or 32
+  const uint32_t t0 = tacc + (uint32_t)(part * C);
+#pragma unroll 1
+  for (int c = 0; c < nck; ++c) {
+    if (!skip_math) {
+      uint32_t r[C];
+      tmem_ld_cols<C>(t0 + (uint32_t)(c * 64), r);
+      tmem_ld_wait_regs<C>(r);
+      epi_chunk<RELU, HEAD>(r, c, c * 64 + part * C, part, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp);
+    }
+    __syncwarp();
+    if (signal && lane == 0) mbar_arrive(&act_ready[c]);
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SW128 operand tiles need 1024 B alignment; plain pointer arithmetic keeps the shared address space visible
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_act = smem + Smem::kActOff;
   uint8_t* s_x0 = smem + Smem::kX0Off;
   uint8_t* s_ring = smem + Smem::kRingOff;
@@ -68,12 +204,14 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   uint64_t* x0pos_empty = x0pos_full + 1;
   uint64_t* x0dir_full = x0pos_empty + 1;
   uint64_t* x0dir_empty = x0dir_full + 1;
+  uint64_t* store_done = x0dir_empty + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::kTmemPtrOff);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_tiles = (prm.P + 127) / 128;
   const int NL = prm.n_layers;
+  const bool save = prm.save != 0;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < NL; ++l) tma_prefetch_desc(&maps.w[l]);
@@ -88,13 +226,14 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], kEpiWarps);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps);
     mbar_init(x0pos_full, 1);
     mbar_init(x0pos_empty, 1);
     mbar_init(x0dir_full, 1);
     mbar_init(x0dir_empty, 1);
+    mbar_init(store_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
@@ -109,16 +248,19 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
+  // NOTE: the producer / MMA / store loops run warp-uniformly (all 32 lanes take the same path and poll the same
+  // barriers); only the asynchronous issue itself is predicated on one elected lane.  That keeps descriptors and
+  // addresses in uniform registers instead of a per-instruction register->uniform "waterfall".
   if (warp == 0) {
     // ====================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        if (it == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (it == 0) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(x0pos_full, kChunkBytes);
           tma_load_2d(s_x0, &maps.x0, x0pos_full, 0, tile * 128);
           if (prm.uses_dir) {
@@ -126,92 +268,151 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
             tma_load_2d(s_x0 + kChunkBytes, &maps.x0, x0dir_full, prm.x0_dir_col, tile * 128);
           }
         }
-        for (int l = 0; l < NL; ++l) {
-          const int N = prm.L[l].N;
-          for (int s = 0; s < prm.L[l].n_slabs; ++s) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* dst = s_ring + stage * kSlabBytes;
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)N * 128);
-            tma_load_2d(dst, &maps.w[l], &full[stage], s * 64, 0);
-            if (N > 128) tma_load_2d(dst + 128 * 128, &maps.w[l], &full[stage], s * 64, 128);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        __syncwarp();
+      }
+      for (int l = 0; l < NL; ++l) {
+        const int N = prm.L[l].N;
+        const int nsl = prm.L[l].n_slabs;
+        for (int s = 0; s < nsl; ++s) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = s_ring + stage * kSlabBytes;
+          if (elect_one()) {
+            if (prm.dbg & 1) {  // experiment: no weight traffic (operands are whatever the ring holds)
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)N * 128);
+              tma_load_2d(dst, &maps.w[l], &full[stage], s * 64, 0);
+              if (N > 128) tma_load_2d(dst + 128 * 128, &maps.w[l], &full[stage], s * 64, 128);
+            }
           }
-          if (l == 1 && it > 0 && prm.uses_dir) {
-            // this tile's view-dir chunk: the previous tile's dir-layer MMAs must have finished reading the buffer
-            mbar_wait(x0dir_empty, (uint32_t)((it - 1) & 1));
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (l == 1 && it > 0 && prm.uses_dir) {
+          // this tile's view-dir chunk: the previous tile's dir-layer MMAs must have finished reading the buffer
+          mbar_wait(x0dir_empty, (uint32_t)((it - 1) & 1));
+          if (elect_one()) {
             mbar_arrive_expect_tx(x0dir_full, kChunkBytes);
             tma_load_2d(s_x0 + kChunkBytes, &maps.x0, x0dir_full, prm.x0_dir_col, tile * 128);
           }
-          if (l == prm.pos_prefetch_layer) {
-            const int ntile = tile + gridDim.x;
-            if (ntile < num_tiles) {  // next tile's position chunk, once this tile's last reader (skip layer) is done
-              mbar_wait(x0pos_empty, (uint32_t)(it & 1));
+          __syncwarp();
+        }
+        if (l == prm.pos_prefetch_layer) {
+          const int ntile = tile + gridDim.x;
+          if (ntile < num_tiles) {  // next tile's position chunk, once this tile's last reader (skip layer) is done
+            mbar_wait(x0pos_empty, (uint32_t)(it & 1));
+            if (elect_one()) {
               mbar_arrive_expect_tx(x0pos_full, kChunkBytes);
               tma_load_2d(s_x0, &maps.x0, x0pos_full, 0, ntile * 128);
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ====================================================== MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      uint32_t lcount = 0;
-      uint32_t rc[4] = {0, 0, 0, 0};
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        bool pos_waited = false, dir_waited = false;
-        for (int l = 0; l < NL; ++l, ++lcount) {
-          const int as = lcount & 1;
-          const uint32_t aphase = (lcount >> 1) & 1;
-          const int N = prm.L[l].N;
-          const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-          mbar_wait(&tempty[as], aphase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    uint32_t lcount = 0;
+    uint32_t acbits = 0;  // bit c = parity of the number of signals so far on act_ready[c] (same replay in every role)
+    const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && lane == 0;
+    const uint32_t act_base = smem_u32(s_act), x0_base = smem_u32(s_x0), ring_base = smem_u32(s_ring);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      bool pos_waited = false, dir_waited = false;
+      for (int l = 0; l < NL; ++l, ++lcount) {
+        const int as = lcount & 1;
+        const uint32_t aphase = (lcount >> 1) & 1;
+        const int N = prm.L[l].N;
+        const int nsl = prm.L[l].n_slabs;
+        const uint32_t srcs = prm.L[l].src_packed;
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        trace(tr_on, 0, it, l, 0);
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int s = 0; s < nsl; ++s) {
+          const int src = (int)((srcs >> (4 * s)) & 15u);
+          uint32_t a_addr;
+          if (src == kSrcPos) {
+            if (!pos_waited) { mbar_wait(x0pos_full, (uint32_t)(it & 1)); pos_waited = true; }
+            a_addr = x0_base;
+          } else if (src == kSrcDir) {
+            if (!dir_waited) { mbar_wait(x0dir_full, (uint32_t)(it & 1)); dir_waited = true; }
+            a_addr = x0_base + kChunkBytes;
+          } else {
+            mbar_wait(&act_ready[src], ((acbits >> src) & 1u) ^ 1u);  // chunk written by the previous layer's epilogue
+            a_addr = act_base + src * kChunkBytes;
+          }
+          mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * 256;
-          for (int s = 0; s < prm.L[l].n_slabs; ++s) {
-            const int src = prm.L[l].src[s];
-            uint32_t a_addr;
-            if (src == kSrcPos) {
-              if (!pos_waited) { mbar_wait(x0pos_full, (uint32_t)(it & 1)); pos_waited = true; }
-              a_addr = smem_u32(s_x0);
-            } else if (src == kSrcDir) {
-              if (!dir_waited) { mbar_wait(x0dir_full, (uint32_t)(it & 1)); dir_waited = true; }
-              a_addr = smem_u32(s_x0 + kChunkBytes);
-            } else {
-              mbar_wait(&act_ready[src], rc[src] & 1);
-              rc[src]++;
-              a_addr = smem_u32(s_act + src * kChunkBytes);
-            }
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(s_ring + stage * kSlabBytes);
-            const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024);
+          if (s == 0) trace(tr_on, 0, it, l, 1);
+          if (s == nsl - 1) trace(tr_on, 0, it, l, 2);
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(ring_base + stage * kSlabBytes, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (s | k) != 0);
             umma_commit(&empty[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) {
           umma_commit(&tfull[as]);
           if (l == prm.pos_last_layer) umma_commit(x0pos_empty);
           if (l == prm.dir_layer) umma_commit(x0dir_empty);
         }
+        __syncwarp();
+        trace(tr_on, 0, it, l, 3);
+        if (prm.L[l].feeds_next || save) acbits ^= (N > 128 ? 0xFu : 0x3u);
       }
     }
-  } else {
-    // ====================================================== epilogue (8 warps)
-    const int q = warp & 3;
-    const int g = (warp - 2) >> 2;              // column group
+  } else if (warp == 2) {
+    // ====================================================== activation-store issuer (training)
+    if (save) {
+      uint32_t acbits = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int l = 0; l < NL; ++l) {
+          const int nck = prm.L[l].N / 64;
+          const int kind = prm.L[l].save_kind;
+          const int row0 = prm.L[l].save_row0 + tile * 128;
+          for (int c = 0; c < nck; ++c) {
+            mbar_wait(&act_ready[c], (acbits >> c) & 1u);
+            if (elect_one()) {
+              if (kind == 1) tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, row0);
+              else if (kind == 2) tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
+          acbits ^= (nck == 4 ? 0xFu : 0x3u);
+          if (elect_one()) {
+            tma_store_wait_read<0>();  // the epilogue of the next layer may overwrite the chunks
+            mbar_arrive(store_done);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) tma_store_wait<0>();
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ====================================================== epilogue
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int part = (warp - kEpiWarp0) >> 2;        // which kEpiCols columns of every 64-column chunk
     const int row_local = q * 32 + lane;
-    const bool gleader = ((warp - 2) & 3) == 0 && lane == 0;  // one thread per group issues barriers' side effects
     const uint32_t swz = (uint32_t)(row_local & 7);
-    const int bar_id = 1 + g;
+    const uint32_t act_row_addr = smem_u32(s_act) + (uint32_t)row_local * 128u;
+    const uint32_t bias_base = smem_u32(s_bias);
+    const uint32_t w7_addr = smem_u32(s_w7), wrgb_addr = smem_u32(s_wrgb);
+    const bool skip_math = (prm.dbg & 2) != 0;
     uint32_t lcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int row = tile * 128 + row_local;
       float hp[8];  // head-7 partial dot products over this thread's columns
 #pragma unroll
@@ -220,102 +421,87 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
       for (int l = 0; l < NL; ++l, ++lcount) {
         const int as = lcount & 1;
         const uint32_t aphase = (lcount >> 1) & 1;
-        const int N = prm.L[l].N;
-        const int relu = prm.L[l].relu;
-        const int nck = (N == 256) ? 2 : 1;
+        const int nck = prm.L[l].N / 64;
+        const bool signal = prm.L[l].feeds_next || save;
+        // the TMA stores of the previous layer's chunks must have finished reading shared memory
+        if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
         mbar_wait(&tfull[as], aphase);
         tc_fence_after();
-        if (prm.save) {  // stores issued from this group's chunks must have finished reading shared memory
-          if (gleader) tma_store_wait_read<0>();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        }
-        const float* bias = s_bias + l * 256;
-        for (int ci = 0; ci < nck; ++ci) {
-          const int c = (N == 256) ? (2 * g + ci) : g;
-          uint8_t* so = s_act + c * kChunkBytes + row_local * 128;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c0 = c * 64 + h * 32;
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + as * 256 + c0 + ((uint32_t)(q * 32) << 16), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int p4 = 0; p4 < 4; ++p4) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float x = __uint_as_float(r[p4 * 8 + e]) + bias[c0 + p4 * 8 + e];
-                v[e] = relu ? fmaxf(x, 0.0f) : x;
-              }
-              const uint32_t piece = ((uint32_t)(h * 4 + p4) ^ swz) << 4;
-              *reinterpret_cast<uint4*>(so + piece) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                                 pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              if (l == prm.head7_layer) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float xr = round_bf16(v[e]);
-#pragma unroll
-                  for (int o = 0; o < 8; ++o)
-                    if (o < prm.head7_n) hp[o] += xr * s_w7[o * 256 + c0 + p4 * 8 + e];
-                }
-              }
-              if (l == prm.rgb_layer) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float xr = round_bf16(v[e]);
-                  const int col = c0 + p4 * 8 + e;
-                  rgbp[0] += xr * s_wrgb[col];
-                  rgbp[1] += xr * s_wrgb[128 + col];
-                  rgbp[2] += xr * s_wrgb[256 + col];
-                }
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (gleader) {
-            if (prm.L[l].feeds_next) mbar_arrive(&act_ready[c]);
-            if (prm.save && prm.L[l].save_kind == 1) {
-              tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, prm.L[l].save_row0 + tile * 128);
-              tma_store_commit();
-            } else if (prm.save && prm.L[l].save_kind == 2) {
-              tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
-              tma_store_commit();
-            }
-          }
-        }
+        trace(tr_on, 1, it, l, 0);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
+        const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
+        if (l == prm.head7_layer && prm.head7_n == 1)
+          epi_layer<true, 1>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, w7_addr, 1, hp,
+                             rgbp, skip_math);
+        else if (l == prm.head7_layer)
+          epi_layer<true, 3>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, w7_addr,
+                             prm.head7_n, hp, rgbp, skip_math);
+        else if (l == prm.rgb_layer)
+          epi_layer<true, 2>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, wrgb_addr, 0, hp,
+                             rgbp, skip_math);
+        else if (prm.L[l].relu)
+          epi_layer<true, 0>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0, 0, hp, rgbp,
+                             skip_math);
+        else
+          epi_layer<false, 0>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0, 0, hp, rgbp,
+                              skip_math);
+        trace(tr_on, 1, it, l, 2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
+        trace(tr_on, 1, it, l, 3);
       }
-      // ---- register heads: combine the two column groups' partial sums and write the raw outputs
-      float* xr = s_xchg + row_local * 12;
-      if (g == 1) {
+      // ---- register heads: combine the column parts' partial sums (4 values per pass) and write the raw outputs
+      const bool vd = prm.rgb_layer >= 0;
+      const int nvals = vd ? 4 : prm.head7_n;
+      float tot[8];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) xr[o] = hp[o];
-        xr[8] = rgbp[0];
-        xr[9] = rgbp[1];
-        xr[10] = rgbp[2];
+      for (int o = 0; o < 8; ++o) tot[o] = 0.0f;
+      for (int pass = 0; pass * 4 < nvals; ++pass) {
+        float v4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float x = 0.0f;
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (o == pass * 4 + j) x = hp[o];
+          v4[j] = x;
+        }
+        if (vd) { v4[0] = rgbp[0]; v4[1] = rgbp[1]; v4[2] = rgbp[2]; v4[3] = hp[0]; }
+        if (part > 0)
+          *reinterpret_cast<float4*>(s_xchg + ((part - 1) * 128 + row_local) * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (part == 0) {
+#pragma unroll
+          for (int pp = 0; pp < kEpiWarps / 4 - 1; ++pp) {
+            const float4 t = *reinterpret_cast<const float4*>(s_xchg + (pp * 128 + row_local) * 4);
+            v4[0] += t.x; v4[1] += t.y; v4[2] += t.z; v4[3] += t.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+              if (o == pass * 4 + j) tot[o] = v4[j];
+        }
+        if ((pass + 1) * 4 < nvals) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
-      asm volatile("bar.sync 3, 256;" ::: "memory");
-      if (g == 0 && row < prm.P) {
+      if (part == 0 && row < prm.P) {
         float* o_row = prm.out + (size_t)row * prm.out_cols;
-        if (prm.rgb_layer >= 0) {
+        if (vd) {
           const float* pb = prm.params;
           float4 o4;
-          o4.x = rgbp[0] + xr[8] + pb[prm.rgb_b_off + 0];
-          o4.y = rgbp[1] + xr[9] + pb[prm.rgb_b_off + 1];
-          o4.z = rgbp[2] + xr[10] + pb[prm.rgb_b_off + 2];
-          o4.w = hp[0] + xr[0] + pb[prm.head7_b_off];
+          o4.x = tot[0] + __ldg(pb + prm.rgb_b_off + 0);
+          o4.y = tot[1] + __ldg(pb + prm.rgb_b_off + 1);
+          o4.z = tot[2] + __ldg(pb + prm.rgb_b_off + 2);
+          o4.w = tot[3] + __ldg(pb + prm.head7_b_off);
           *reinterpret_cast<float4*>(o_row) = o4;
         } else {
 #pragma unroll
           for (int o = 0; o < 8; ++o)
-            if (o < prm.head7_n) o_row[o] = hp[o] + xr[o] + prm.params[prm.head7_b_off + o];
+            if (o < prm.head7_n) o_row[o] = tot[o] + __ldg(prm.params + prm.head7_b_off + o);
         }
       }
     }
-    if (gleader) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -326,8 +512,14 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
 
 namespace nmx {
 
-int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream) {
-  if (prm.P <= 0) return 0;
+int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm_in, cudaStream_t stream) {
+  if (prm_in.P <= 0) return 0;
+  ChainParams prm = prm_in;
+  for (int l = 0; l < prm.n_layers; ++l) {
+    uint32_t pk = 0;
+    for (int s = 0; s < prm.L[l].n_slabs; ++s) pk |= (uint32_t)(prm.L[l].src[s] & 15) << (4 * s);
+    prm.L[l].src_packed = pk;
+  }
   static bool attr = false;
   if (!attr) {
     NMX_CUDA(cudaFuncSetAttribute(mlp_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kAlloc));
@@ -341,3 +533,10 @@ int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t
 }
 
 }  // namespace nmx
+
+// diagnostics: copies the event trace recorded under NMX_CHAIN_DBG bit 2 (n int64 values) to host memory
+extern "C" int nmx_chain_trace_read(long long* out, int n) {
+  NMX_CHECK_ARG(out && n > 0 && (size_t)n * 8 <= sizeof(g_trace), "out non-null; 0 < n <= trace size");
+  NMX_CUDA(cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 8));
+  return 0;
+}

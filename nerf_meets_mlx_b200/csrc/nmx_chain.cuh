@@ -13,6 +13,7 @@ constexpr int kSrcDir = 5;  // A slab = encoded-view-dir chunk of the input tile
 struct ChainLayerDesc {
   int n_slabs;     // K / 64
   int src[5];      // A-operand source of every K slab
+  uint32_t src_packed;  // the same, 4 bits per slab (filled by launch_chain_fwd)
   int N;           // 256 or 128
   int relu;
   int bias_off;    // float offset into params
@@ -32,6 +33,7 @@ struct ChainParams {
   int rgb_layer, rgb_w_off, rgb_b_off;                 // rgb head from the dir layer's output, or rgb_layer = -1
   int uses_dir, x0_dir_col;
   int pos_last_layer, pos_prefetch_layer, dir_layer;
+  int dbg;  // experiments only (NMX_CHAIN_DBG): bit 0 = no weight TMA traffic, bit 1 = epilogue math skipped
 };
 
 struct ChainMaps {

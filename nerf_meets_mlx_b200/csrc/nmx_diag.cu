@@ -1,0 +1,73 @@
+// Diagnostics (not on the product path): raw tcgen05.mma issue-rate probe used to calibrate the MLP kernels' roofline.
+// Every CTA issues `iters` back-to-back M=128 x N x K=16 bf16 MMAs on resident shared-memory operands (no TMA, no
+// epilogue) and reports SM clocks and nanoseconds, so the per-SM MMA period and the clock the chip sustains under a
+// full-chip tensor load can be read directly.
+#include "nmx_common.cuh"
+#include "nmx_sm100.cuh"
+
+using namespace nmx;
+using namespace nmx::sm100;
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(int N, int iters, int n_slabs, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  // A: 128 x 64 bf16 (16 KB), B slabs: n_slabs x (256 x 64 bf16 = 32 KB); pseudo-random bf16 values in [-1, 1)
+  const int total_words = (16384 + n_slabs * 32768) / 4;
+  uint32_t x = 0x9E3779B9u * (threadIdx.x + 1) + blockIdx.x;
+  for (int i = threadIdx.x; i < total_words; i += blockDim.x) {
+    x = x * 1664525u + 1013904223u;
+    uint32_t lo = 0x3C00u | ((x >> 9) & 0x83FFu), hi = 0x3C00u | ((x >> 20) & 0x83FFu);
+    reinterpret_cast<uint32_t*>(smem)[i] = lo | (hi << 16);
+  }
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc<512>(&tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint32_t a_addr = smem_u32(smem);
+    long long c0 = clock64();
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    for (int i = 0; i < iters; ++i) {
+      const int slab = (i >> 2) % n_slabs;
+      const int k = i & 3;
+      const uint64_t adesc = make_smem_desc(a_addr, 16, 1024) + (uint64_t)(k * 2);
+      const uint64_t bdesc = make_smem_desc(a_addr + 16384 + slab * 32768, 16, 1024) + (uint64_t)(k * 2);
+      umma_bf16(tmem_base + ((i >> 4) & 1) * 256, adesc, bdesc, idesc, (i & 15) != 0);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    out[blockIdx.x * 2 + 0] = c1 - c0;
+    out[blockIdx.x * 2 + 1] = (long long)(g1 - g0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+// out: int64 [2 * ctas] device buffer = (SM clocks, nanoseconds) per CTA
+extern "C" int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream) {
+  NMX_CHECK_ARG(out && (N == 64 || N == 128 || N == 256) && iters > 0 && n_slabs >= 1 && n_slabs <= 6 && ctas > 0,
+                "N in {64,128,256}; iters > 0; 1 <= n_slabs <= 6; ctas > 0");
+  const int smem_bytes = 16384 + n_slabs * 32768 + 1024;
+  NMX_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(N, iters, n_slabs, out);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}

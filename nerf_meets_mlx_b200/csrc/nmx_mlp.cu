@@ -678,6 +678,11 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   for (int l = nl; l < kMaxChainLayers; ++l) maps.w[l] = maps.w[0];
   prm.n_layers = nl;
   prm.pos_prefetch_layer = prm.pos_last_layer + 2 < nl ? prm.pos_last_layer + 2 : nl - 1;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
+    prm.dbg = dbg;
+  }
   prm.P = (int)npts; prm.save = c.training ? 1 : 0; prm.params = c.params; prm.out = out; prm.out_cols = out_cols;
   if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
   if (c.training) {
