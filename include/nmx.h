@@ -159,10 +159,11 @@ int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t*
 
 /* ---- diagnostics (not on the product path; used by scripts/ to calibrate the roofline) ------------------------
  * nmx_diag_mma_rate: every CTA issues `iters` back-to-back M=128 x N x K=16 bf16 tcgen05 MMAs on resident operands;
- * out[2*cta] = SM clocks, out[2*cta+1] = nanoseconds.
+ * out[2*cta] = SM clocks, out[2*cta+1] = nanoseconds.  mode bits 0-1: 1 = tcgen05.commit after every 4 MMAs,
+ * 2 = commit + an mbarrier poll + fence; bit 2: alternate two 128-column accumulator halves.
  * nmx_chain_trace_read: copies the (clock, ns) event trace the fused MLP chain records for CTA 0 when the environment
  * variable NMX_CHAIN_DBG has bit 2 set. */
-int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream);
+int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream, int mode);
 int nmx_chain_trace_read(long long* out, int n);
 
 #ifdef __cplusplus

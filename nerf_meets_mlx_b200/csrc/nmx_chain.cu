@@ -1,17 +1,21 @@
 // K3 fused forward chain: the whole NeRF MLP (models/NeRF.py:201-243) for a 128-point tile in ONE persistent kernel.
 //
 // Activations never leave the SM between layers: the epilogue of layer l writes relu(acc + b) as bf16 straight into
-// the 128B-swizzled shared-memory tile that is the A operand of layer l+1 (in place, 64-column chunk by chunk, all
-// eight epilogue warps on the same chunk so the MMAs of layer l+1 start as soon as chunk 0 exists), accumulators
-// ping-pong between the two halves of TMEM, and the weights (2.4 MB bf16 per net, L2-resident) stream through a TMA
-// ring in 64-wide K slabs.  The skip concat [input_pos, h] and the view-dir concat [feature, input_dir] are extra K
-// slabs read from the resident encoded-input tile.  The N=1 / N=3 / N<=8 heads (alpha, rgb, output_linear) are
-// evaluated by the epilogue threads from the values they already hold in registers.  When training, a dedicated
-// warp TMA-stores each finished chunk to the saved-activation buffers (the smem tile doubles as the staging buffer).
+// the 128B-swizzled shared-memory tile that is the A operand of layer l+1 (in place), accumulators ping-pong between
+// the two halves of TMEM, and the weights (2.4 MB bf16 per net, L2-resident) stream through a TMA ring.
 //
-// Roles (640 threads): warp 0 = TMA producer (weight ring + encoded-input tile), warp 1 = MMA issuer,
-// warp 2 = activation-store issuer (training only), warps 4..19 = epilogue (four warps per TMEM lane quadrant, each
-// taking 16 of a chunk's 64 columns).
+// Pipelining inside one tile (the layers of a tile are strictly dependent): the epilogue turns the accumulator into
+// the next layer's input in two steps of two 64-column chunks; the MMA warp starts layer l+1 on chunks 0,1 while the
+// epilogue is still producing chunks 2,3.  Every K slab is one "piece" of 4 MMAs M128 x N256 x K16 described by a
+// host-built 64-bit table entry in the constant bank, so the issue loop is a few dozen uniform-datapath instructions.
+// The skip concat [input_pos, h] and the view-dir concat [feature, input_dir] are extra K slabs read from the
+// resident encoded-input tile.  The N=1 / N=3 / N<=8 heads (alpha, rgb, output_linear) are evaluated by the epilogue
+// threads from the values they already hold in registers.  When training, a dedicated warp TMA-stores each finished
+// chunk to the saved-activation buffers (the smem tile doubles as the staging buffer).
+//
+// Roles (608 threads): warps 0..15 = epilogue (four warps per TMEM lane quadrant; in each half-phase two of them
+// share a 64-column chunk, 32 columns each), warp 16 = activation-store issuer (training only), warp 17 = TMA producer
+// (weight ring + encoded-input tile), warp 18 = MMA issuer.
 // Roofline: tensor pipe (inference: ~0 HBM traffic; training: 512 B/point/layer of activation stores).
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
@@ -23,11 +27,16 @@ using namespace nmx::sm100;
 namespace {
 
 constexpr int kEpiWarps = 16;               // 4 per TMEM lane quadrant
-constexpr int kEpiCols = 64 / (kEpiWarps / 4);  // columns of a 64-column chunk one epilogue warp handles (16 or 32)
-constexpr int kEpiWarp0 = 4;                // warps 0 TMA, 1 MMA, 2 activation store + TMEM alloc, 3 idle, 4.. epilogue
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kEpiCols = 32;                // columns one epilogue warp handles per half-phase
+// Warp roles.  The issue scheduler favours the highest warp id on a sub-partition, so the latency-critical single
+// issuers (MMA, TMA) sit above the sixteen epilogue warps they share the SM with.
+constexpr int kEpiWarp0 = 0;                // warps 0..15 epilogue (TMEM lane quadrant = warp % 4)
+constexpr int kStoreWarp = 16;              // activation-store issuer (training) + TMEM alloc/dealloc
+constexpr int kTmaWarp = 17;
+constexpr int kMmaWarp = 18;
+constexpr int kThreads = 19 * 32;
 constexpr int kStages = 3;
-constexpr int kSlabBytes = 256 * 64 * 2;   // one 64-wide K slab of a 256-row weight matrix
+constexpr int kSlabBytes = 256 * 64 * 2;   // one piece of weights: up to 256 output rows x 64-wide K slab
 constexpr int kChunkBytes = 128 * 64 * 2;  // one 128-row x 64-col bf16 activation chunk
 
 struct Smem {
@@ -39,9 +48,9 @@ struct Smem {
   static constexpr int kWrgbOff = kW7Off + 8 * 256 * 4;                  // rgb weights [3][128] fp32
   static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                // [3][128][4] fp32 partial sums
   static constexpr int kBarOff = kXchgOff + 3 * 128 * 4 * 4;
-  // barriers: full[S], empty[S], tfull[2], tempty[2], act_ready[4], x0pos_full, x0pos_empty, x0dir_full, x0dir_empty,
-  //           store_done
-  static constexpr int kNumBars = 2 * kStages + 2 + 2 + 4 + 4 + 1;
+  // barriers: full[S], empty[S], tfull[2 stages][2 halves], tempty[2], act_ready[4], x0pos_full, x0pos_empty,
+  //           x0dir_full, x0dir_empty, store_done
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 + 4 + 4 + 1;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kAlloc = kTotal + 1024;
@@ -63,6 +72,25 @@ __device__ __forceinline__ void trace(bool on, int role, int it, int l, int ev) 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// packed fp32x2 add (sm_100: one FADD2 for two columns) and fp32x2 -> bf16x2 conversion with the ReLU folded in
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+template <bool RELU>
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {  // low half <- low float, high half <- high float
+  uint32_t lo, hi, d;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -104,30 +132,25 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
 // TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand of the next layer / TMA-store source),
 // optional register heads.  HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
 // The TMEM load of chunk c+1 is issued before the math of chunk c (two register sets).
-// math + store of one chunk's columns held in r[] (fp32 accumulators of this thread's row)
+// math + store of 32 columns [c0, c0 + 32) of chunk c held in r[] (fp32 accumulators of this thread's row)
 template <bool RELU, int HEAD>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&r)[kEpiCols], const int c, const int c0, const int part,
-                                          const uint32_t bias_addr, const uint32_t act_row_addr, const uint32_t swz,
-                                          const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3]) {
-  constexpr int C = kEpiCols;
-  float4 b[C / 4];
-#pragma unroll
-  for (int i = 0; i < C / 4; ++i) b[i] = lds128(bias_addr + (uint32_t)(c0 + i * 4) * 4u);
+__device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
+                                         const uint32_t bias_addr, const uint32_t act_row_addr, const uint32_t swz,
+                                         const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3]) {
   const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
 #pragma unroll
-  for (int p4 = 0; p4 < C / 8; ++p4) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float4 bb = b[p4 * 2 + (e >> 2)];
-      const float be = (e & 3) == 0 ? bb.x : (e & 3) == 1 ? bb.y : (e & 3) == 2 ? bb.z : bb.w;
-      const float x = __uint_as_float(r[p4 * 8 + e]) + be;
-      v[e] = RELU ? fmaxf(x, 0.0f) : x;
-    }
+  for (int p4 = 0; p4 < 4; ++p4) {
+    const float4 b0 = lds128(bias_addr + (uint32_t)(c0 + p4 * 8) * 4u);
+    const float4 b1 = lds128(bias_addr + (uint32_t)(c0 + p4 * 8 + 4) * 4u);
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
-    sts128(so + ((((uint32_t)(part * (C / 8) + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+    for (int e = 0; e < 4; ++e) {  // bf16(relu(acc + bias)): fp32 add, ReLU folded into the rounding conversion
+      const uint64_t x = add_f32x2(pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]),
+                                   pack64(__float_as_uint(bv[2 * e]), __float_as_uint(bv[2 * e + 1])));
+      pk[e] = cvt_bf16x2<RELU>(x);
+    }
+    sts128(so + ((((uint32_t)(sub * 4 + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
     if (HEAD != 0) {
       float xr[8];  // the bf16-rounded activations (what a separate head kernel would read back)
 #pragma unroll
@@ -160,26 +183,36 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&r)[kEpiCols], const i
   fence_proxy_async_smem();
 }
 
-// Epilogue of one layer for one warp: for every 64-column chunk, this warp's kEpiCols columns x 32 rows:
-// TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand of the next layer / TMA-store source),
-// optional register heads.  HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
+// Epilogue of one layer for one warp.  Half-phase h (accumulator columns [128h, 128h+128) = chunks 2h, 2h+1):
+// this warp takes 32 columns of one of the two chunks: TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand
+// of the next layer / TMA-store source), optional register heads.
+// HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
 template <bool RELU, int HEAD>
-__device__ __forceinline__ void epi_layer(const uint32_t tacc, const int nck, const int part, const uint32_t bias_addr,
-                                          const uint32_t act_row_addr, const uint32_t swz, uint64_t* act_ready,
-                                          const bool signal, const int lane, const uint32_t hw_addr, const int head_n,
-                                          float (&hp)[8], float (&rgbp)[3], const bool skip_math) {
-  constexpr int C = kEpiCols;  // 16 or 32
-  const uint32_t t0 = tacc + (uint32_t)(part * C);
+__device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halves, uint64_t* tfull2, const uint32_t aphase,
+                                          const int part, const uint32_t bias_addr, const uint32_t act_row_addr,
+                                          const uint32_t swz, uint64_t* act_ready, const bool signal, const int lane,
+                                          const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3],
+                                          const bool skip_math, const bool tr_on, const int it, const int l) {
 #pragma unroll 1
-  for (int c = 0; c < nck; ++c) {
-    if (!skip_math) {
-      uint32_t r[C];
-      tmem_ld_cols<C>(t0 + (uint32_t)(c * 64), r);
-      tmem_ld_wait_regs<C>(r);
-      epi_chunk<RELU, HEAD>(r, c, c * 64 + part * C, part, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp);
+  for (int h = 0; h < 2; ++h) {
+    mbar_wait(&tfull2[h], aphase);
+    if (h == 0) trace(tr_on, 1, it, l, 0);
+    if (h < n_halves) {
+      tc_fence_after();
+      const int c = 2 * h + (part >> 1);
+      const int sub = part & 1;
+      const int c0 = c * 64 + sub * 32;
+      if (!skip_math) {
+        uint32_t r[32];
+        tmem_ld_32x32(tacc + (uint32_t)c0, r);
+        tmem_ld_wait_regs<32>(r);
+        if (h == 0) trace(tr_on, 1, it, l, 1);
+        epi_cols<RELU, HEAD>(r, c, c0, sub, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp);
+      }
+      __syncwarp();
+      if (signal && lane == 0) mbar_arrive(&act_ready[c]);
+      if (h == 0) trace(tr_on, 1, it, l, 2);
     }
-    __syncwarp();
-    if (signal && lane == 0) mbar_arrive(&act_ready[c]);
   }
 }
 
@@ -197,8 +230,8 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   float* s_xchg = reinterpret_cast<float*>(smem + Smem::kXchgOff);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Smem::kBarOff);
   uint64_t* empty = full + kStages;
-  uint64_t* tfull = empty + kStages;
-  uint64_t* tempty = tfull + 2;
+  uint64_t* tfull = empty + kStages;   // [acc stage][half]
+  uint64_t* tempty = tfull + 4;
   uint64_t* act_ready = tempty + 2;
   uint64_t* x0pos_full = act_ready + 4;
   uint64_t* x0pos_empty = x0pos_full + 1;
@@ -213,22 +246,20 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   const int NL = prm.n_layers;
   const bool save = prm.save != 0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     for (int l = 0; l < NL; ++l) tma_prefetch_desc(&maps.w[l]);
     tma_prefetch_desc(&maps.x0);
     tma_prefetch_desc(&maps.save);
     tma_prefetch_desc(&maps.hd);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
-    }
-    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&tfull[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&tempty[i], kEpiWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps / 2);
     mbar_init(x0pos_full, 1);
     mbar_init(x0pos_empty, 1);
     mbar_init(x0dir_full, 1);
@@ -236,7 +267,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     mbar_init(store_done, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  if (warp == kStoreWarp) tmem_alloc<512>(tmem_ptr);
   // stage biases and the register-head weights (fp32) once per CTA
   for (int i = threadIdx.x; i < NL * 256; i += kThreads) {
     int l = i >> 8, c = i & 255;
@@ -253,7 +284,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   // NOTE: the producer / MMA / store loops run warp-uniformly (all 32 lanes take the same path and poll the same
   // barriers); only the asynchronous issue itself is predicated on one elected lane.  That keeps descriptors and
   // addresses in uniform registers instead of a per-instruction register->uniform "waterfall".
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ====================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -271,18 +302,19 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
         __syncwarp();
       }
       for (int l = 0; l < NL; ++l) {
+        const int np = prm.L[l].n_pieces;
         const int N = prm.L[l].N;
-        const int nsl = prm.L[l].n_slabs;
-        for (int s = 0; s < nsl; ++s) {
+        for (int i = 0; i < np; ++i) {
+          const uint32_t hi = (uint32_t)(prm.L[l].piece_tab[i] >> 32);  // weight box: k column
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = s_ring + stage * kSlabBytes;
           if (elect_one()) {
             if (prm.dbg & 1) {  // experiment: no weight traffic (operands are whatever the ring holds)
               mbar_arrive(&full[stage]);
             } else {
-              mbar_arrive_expect_tx(&full[stage], (uint32_t)N * 128);
-              tma_load_2d(dst, &maps.w[l], &full[stage], s * 64, 0);
-              if (N > 128) tma_load_2d(dst + 128 * 128, &maps.w[l], &full[stage], s * 64, 128);
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)N * 128u);
+              tma_load_2d(dst, &maps.w[l], &full[stage], (int)(hi & 0xffffu), 0);
+              if (N > 128) tma_load_2d(dst + 128 * 128, &maps.w[l], &full[stage], (int)(hi & 0xffffu), 128);
             }
           }
           __syncwarp();
@@ -310,67 +342,69 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ====================================================== MMA issuer
+    // Per piece: one 64-bit table entry from the constant bank (host-built, see launch_chain_fwd), at most two
+    // barrier waits, four MMAs and their commits -- everything else was folded into the table.
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     uint32_t lcount = 0;
     uint32_t acbits = 0;  // bit c = parity of the number of signals so far on act_ready[c] (same replay in every role)
     const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && lane == 0;
-    const uint32_t act_base = smem_u32(s_act), x0_base = smem_u32(s_x0), ring_base = smem_u32(s_ring);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    const uint32_t ring16 = smem_u32(s_ring) >> 4;
+    constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      bool pos_waited = false, dir_waited = false;
       for (int l = 0; l < NL; ++l, ++lcount) {
         const int as = lcount & 1;
         const uint32_t aphase = (lcount >> 1) & 1;
-        const int N = prm.L[l].N;
-        const int nsl = prm.L[l].n_slabs;
-        const uint32_t srcs = prm.L[l].src_packed;
-        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+        const int np = prm.L[l].n_pieces;
+        const uint32_t idesc = make_idesc_bf16(128, prm.L[l].N, 0, 0);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         trace(tr_on, 0, it, l, 0);
-        const uint32_t d_tmem = tmem_base + as * 256;
-        for (int s = 0; s < nsl; ++s) {
-          const int src = (int)((srcs >> (4 * s)) & 15u);
-          uint32_t a_addr;
-          if (src == kSrcPos) {
-            if (!pos_waited) { mbar_wait(x0pos_full, (uint32_t)(it & 1)); pos_waited = true; }
-            a_addr = x0_base;
-          } else if (src == kSrcDir) {
-            if (!dir_waited) { mbar_wait(x0dir_full, (uint32_t)(it & 1)); dir_waited = true; }
-            a_addr = x0_base + kChunkBytes;
-          } else {
-            mbar_wait(&act_ready[src], ((acbits >> src) & 1u) ^ 1u);  // chunk written by the previous layer's epilogue
-            a_addr = act_base + src * kChunkBytes;
-          }
+        const uint32_t tacc = tmem_base + as * 256;
+        for (int i = 0; i < np; ++i) {
+          const uint64_t e = prm.L[l].piece_tab[i];
+          const uint32_t lo = (uint32_t)e;
           mbar_wait(&full[stage], phase);
+          if (i == 0) trace(tr_on, 0, it, l, 1);
+          const uint32_t wc = (lo >> 25) & 7u;
+          if (wc == 1) {  // first use of an activation chunk written by the previous layer's epilogue
+            const uint32_t c = (lo >> 28) & 3u;
+            mbar_wait(&act_ready[c], ((acbits >> c) & 1u) ^ 1u);
+          } else if (wc == 2) {
+            mbar_wait(x0pos_full, (uint32_t)(it & 1));
+          } else if (wc == 3) {
+            mbar_wait(x0dir_full, (uint32_t)(it & 1));
+          }
           tc_fence_after();
-          if (s == 0) trace(tr_on, 0, it, l, 1);
-          if (s == nsl - 1) trace(tr_on, 0, it, l, 2);
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(ring_base + stage * kSlabBytes, 16, 1024);
+          if (i == 0) trace(tr_on, 0, it, l, 2);
+          const uint64_t adesc = kDescHi | (uint64_t)(((smem16 + (lo & 0xffffu)) & 0x3fffu) | 0x10000u);
+          const uint64_t bdesc = kDescHi | (uint64_t)(((ring16 + (uint32_t)stage * (kSlabBytes >> 4)) & 0x3fffu) | 0x10000u);
+          const uint32_t d_tmem = tacc + ((lo >> 16) & 0xffu);
           if (elect_one()) {
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (lo >> 24) & 1u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (s | k) != 0);
+            for (int k = 1; k < 4; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
             umma_commit(&empty[stage]);
+            if (lo & (1u << 30)) umma_commit(&tfull[as * 2 + 0]);
+            if (lo & (1u << 31)) umma_commit(&tfull[as * 2 + 1]);
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) {
-          umma_commit(&tfull[as]);
           if (l == prm.pos_last_layer) umma_commit(x0pos_empty);
           if (l == prm.dir_layer) umma_commit(x0dir_empty);
         }
         __syncwarp();
         trace(tr_on, 0, it, l, 3);
-        if (prm.L[l].feeds_next || save) acbits ^= (N > 128 ? 0xFu : 0x3u);
+        if (prm.L[l].feeds_next || save) acbits ^= (prm.L[l].N > 128 ? 0xFu : 0x3u);
       }
     }
-  } else if (warp == 2) {
+  } else if (warp == kStoreWarp) {
     // ====================================================== activation-store issuer (training)
     if (save) {
       uint32_t acbits = 0;
@@ -399,10 +433,10 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
     }
-  } else if (warp >= kEpiWarp0) {
-    // ====================================================== epilogue
+  } else {
+    // ====================================================== epilogue (warps 0..15)
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
-    const int part = (warp - kEpiWarp0) >> 2;        // which kEpiCols columns of every 64-column chunk
+    const int part = (warp - kEpiWarp0) >> 2;        // 0..3: chunk (part >> 1) of the half, 32-column sub-block (part & 1)
     const int row_local = q * 32 + lane;
     const uint32_t swz = (uint32_t)(row_local & 7);
     const uint32_t act_row_addr = smem_u32(s_act) + (uint32_t)row_local * 128u;
@@ -411,6 +445,14 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     const bool skip_math = (prm.dbg & 2) != 0;
     uint32_t lcount = 0;
     const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+    const bool vd = prm.rgb_layer >= 0;
+    float hb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // head biases of the view-dir net (rgb, alpha), loaded once
+    if (vd && part == 0) {
+      hb[0] = __ldg(prm.params + prm.rgb_b_off + 0);
+      hb[1] = __ldg(prm.params + prm.rgb_b_off + 1);
+      hb[2] = __ldg(prm.params + prm.rgb_b_off + 2);
+      hb[3] = __ldg(prm.params + prm.head7_b_off);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int row = tile * 128 + row_local;
@@ -421,38 +463,34 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
       for (int l = 0; l < NL; ++l, ++lcount) {
         const int as = lcount & 1;
         const uint32_t aphase = (lcount >> 1) & 1;
-        const int nck = prm.L[l].N / 64;
+        const int n_halves = prm.L[l].N / 128;
         const bool signal = prm.L[l].feeds_next || save;
         // the TMA stores of the previous layer's chunks must have finished reading shared memory
         if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
-        mbar_wait(&tfull[as], aphase);
-        tc_fence_after();
-        trace(tr_on, 1, it, l, 0);
         const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
         const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
+        uint64_t* tf = &tfull[as * 2];
         if (l == prm.head7_layer && prm.head7_n == 1)
-          epi_layer<true, 1>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, w7_addr, 1, hp,
-                             rgbp, skip_math);
+          epi_layer<true, 1>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                             w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l);
         else if (l == prm.head7_layer)
-          epi_layer<true, 3>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, w7_addr,
-                             prm.head7_n, hp, rgbp, skip_math);
+          epi_layer<true, 3>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                             w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l);
         else if (l == prm.rgb_layer)
-          epi_layer<true, 2>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, wrgb_addr, 0, hp,
-                             rgbp, skip_math);
+          epi_layer<true, 2>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                             wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l);
         else if (prm.L[l].relu)
-          epi_layer<true, 0>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0, 0, hp, rgbp,
-                             skip_math);
+          epi_layer<true, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+                             0, hp, rgbp, skip_math, tr_on, it, l);
         else
-          epi_layer<false, 0>(tacc, nck, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0, 0, hp, rgbp,
-                              skip_math);
-        trace(tr_on, 1, it, l, 2);
+          epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+                              0, hp, rgbp, skip_math, tr_on, it, l);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
         trace(tr_on, 1, it, l, 3);
       }
       // ---- register heads: combine the column parts' partial sums (4 values per pass) and write the raw outputs
-      const bool vd = prm.rgb_layer >= 0;
       const int nvals = vd ? 4 : prm.head7_n;
       float tot[8];
 #pragma unroll
@@ -473,7 +511,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         if (part == 0) {
 #pragma unroll
-          for (int pp = 0; pp < kEpiWarps / 4 - 1; ++pp) {
+          for (int pp = 0; pp < 3; ++pp) {
             const float4 t = *reinterpret_cast<const float4*>(s_xchg + (pp * 128 + row_local) * 4);
             v4[0] += t.x; v4[1] += t.y; v4[2] += t.z; v4[3] += t.w;
           }
@@ -488,13 +526,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
       if (part == 0 && row < prm.P) {
         float* o_row = prm.out + (size_t)row * prm.out_cols;
         if (vd) {
-          const float* pb = prm.params;
-          float4 o4;
-          o4.x = tot[0] + __ldg(pb + prm.rgb_b_off + 0);
-          o4.y = tot[1] + __ldg(pb + prm.rgb_b_off + 1);
-          o4.z = tot[2] + __ldg(pb + prm.rgb_b_off + 2);
-          o4.w = tot[3] + __ldg(pb + prm.head7_b_off);
-          *reinterpret_cast<float4*>(o_row) = o4;
+          *reinterpret_cast<float4*>(o_row) = make_float4(tot[0] + hb[0], tot[1] + hb[1], tot[2] + hb[2], tot[3] + hb[3]);
         } else {
 #pragma unroll
           for (int o = 0; o < 8; ++o)
@@ -505,7 +537,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == kStoreWarp) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
@@ -516,9 +548,28 @@ int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm_in, cudaStrea
   if (prm_in.P <= 0) return 0;
   ChainParams prm = prm_in;
   for (int l = 0; l < prm.n_layers; ++l) {
+    ChainLayerDesc& d = prm.L[l];
     uint32_t pk = 0;
-    for (int s = 0; s < prm.L[l].n_slabs; ++s) pk |= (uint32_t)(prm.L[l].src[s] & 15) << (4 * s);
-    prm.L[l].src_packed = pk;
+    for (int s = 0; s < d.n_slabs; ++s) pk |= (uint32_t)(d.src[s] & 15) << (4 * s);
+    d.src_packed = pk;
+    // One piece per 64-wide K slab, full layer width (N = 256 MMAs: a tcgen05.mma costs ~80 clocks to issue whatever
+    // its N, so narrower pieces are issue-bound -- measured with nmx_diag_mma_rate).
+    // Table entry: [0,16) A-operand smem offset >> 4, [16,24) accumulator column, [24] accumulate flag of the first
+    // MMA, [25,28) wait code (0 none, 1 act_ready[chunk in 28-29], 2 pos, 3 dir), [30] / [31] commit "half 0 / 1 of
+    // the accumulator complete" after the piece, [32,48) weight k column.
+    for (int s = 0; s < d.n_slabs; ++s) {
+      const int src = d.src[s];
+      const uint32_t a_off = src == kSrcPos ? Smem::kX0Off : src == kSrcDir ? Smem::kX0Off + kChunkBytes
+                                                                             : Smem::kActOff + src * kChunkBytes;
+      uint64_t e = (uint64_t)(a_off >> 4) | ((uint64_t)(s > 0 ? 1 : 0) << 24);
+      const uint64_t wc = src == kSrcPos ? 2 : src == kSrcDir ? 3 : 1;
+      e |= wc << 25;
+      if (wc == 1) e |= (uint64_t)src << 28;
+      e |= (uint64_t)(s * 64) << 32;
+      if (s == d.n_slabs - 1) e |= (1ull << 30) | (1ull << 31);
+      d.piece_tab[s] = e;
+    }
+    d.n_pieces = d.n_slabs;
   }
   static bool attr = false;
   if (!attr) {

@@ -14,6 +14,9 @@ struct ChainLayerDesc {
   int n_slabs;     // K / 64
   int src[5];      // A-operand source of every K slab
   uint32_t src_packed;  // the same, 4 bits per slab (filled by launch_chain_fwd)
+  // issue schedule of the layer's pieces (filled by launch_chain_fwd; bit layout documented there)
+  uint64_t piece_tab[10];
+  int n_pieces;
   int N;           // 256 or 128
   int relu;
   int bias_off;    // float offset into params

@@ -11,10 +11,11 @@ using namespace nmx::sm100;
 namespace {
 
 __global__ void __launch_bounds__(128, 1)
-mma_rate_kernel(int N, int iters, int n_slabs, long long* out) {
+mma_rate_kernel(int N, int iters, int n_slabs, int mode, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];  // mode >= 1: commit target every 4 MMAs; mode 2: an always-complete barrier that is polled
   __shared__ uint32_t tmem_ptr;
   // A: 128 x 64 bf16 (16 KB), B slabs: n_slabs x (256 x 64 bf16 = 32 KB); pseudo-random bf16 values in [-1, 1)
   const int total_words = (16384 + n_slabs * 32768) / 4;
@@ -27,32 +28,49 @@ mma_rate_kernel(int N, int iters, int n_slabs, long long* out) {
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2[0], 1);
+    mbar_init(&bar2[1], 1);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc<512>(&tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_ptr;
-  if (threadIdx.x == 0) {
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_ptr, 0);
+  if (threadIdx.x < 32) {  // warp-uniform issue loop, one elected lane issues (as in the product kernels)
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint32_t a_addr = smem_u32(smem);
+    const bool alt = (mode & 4) && N <= 128;
     long long c0 = clock64();
     unsigned long long g0, g1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-    for (int i = 0; i < iters; ++i) {
-      const int slab = (i >> 2) % n_slabs;
-      const int k = i & 3;
-      const uint64_t adesc = make_smem_desc(a_addr, 16, 1024) + (uint64_t)(k * 2);
-      const uint64_t bdesc = make_smem_desc(a_addr + 16384 + slab * 32768, 16, 1024) + (uint64_t)(k * 2);
-      umma_bf16(tmem_base + ((i >> 4) & 1) * 256, adesc, bdesc, idesc, (i & 15) != 0);
+    int slab = 0;
+    for (int i = 0; i < iters; i += 4) {
+      if (++slab == n_slabs) slab = 0;
+      const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+      const uint64_t bdesc = make_smem_desc(a_addr + 16384 + slab * 32768, 16, 1024);
+      const uint32_t d = tmem_base + ((i >> 4) & 1) * 256 + (alt ? ((i >> 2) & 1) * 128 : 0);
+      if ((mode & 3) >= 2) {
+        mbar_wait(&bar2[1], 1);  // parity of the phase before the current one: completes immediately
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        umma_bf16(d, adesc, bdesc, idesc, (i & 15) != 0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+        if ((mode & 3) >= 1) umma_commit(&bar2[0]);
+      }
+      __syncwarp();
     }
-    umma_commit(&bar);
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
     mbar_wait(&bar, 0);
     long long c1 = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
-    out[blockIdx.x * 2 + 0] = c1 - c0;
-    out[blockIdx.x * 2 + 1] = (long long)(g1 - g0);
+    if (threadIdx.x == 0) {
+      out[blockIdx.x * 2 + 0] = c1 - c0;
+      out[blockIdx.x * 2 + 1] = (long long)(g1 - g0);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -62,12 +80,12 @@ mma_rate_kernel(int N, int iters, int n_slabs, long long* out) {
 }  // namespace
 
 // out: int64 [2 * ctas] device buffer = (SM clocks, nanoseconds) per CTA
-extern "C" int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream) {
+extern "C" int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream, int mode) {
   NMX_CHECK_ARG(out && (N == 64 || N == 128 || N == 256) && iters > 0 && n_slabs >= 1 && n_slabs <= 6 && ctas > 0,
                 "N in {64,128,256}; iters > 0; 1 <= n_slabs <= 6; ctas > 0");
   const int smem_bytes = 16384 + n_slabs * 32768 + 1024;
   NMX_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(N, iters, n_slabs, out);
+  mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(N, iters, n_slabs, mode, out);
   NMX_LAUNCH_CHECK();
   return 0;
 }

@@ -13,7 +13,7 @@ out = torch.zeros(2 * 148, dtype=torch.int64, device="cuda")
 for ctas in (1, 148):
     for N, slabs in ((256, 1), (256, 3), (128, 3)):
         for _ in range(2):
-            L.call("nmx_diag_mma_rate", L.i32(N), L.i32(20000), L.i32(slabs), L.i32(ctas), L.ptr(out), L.stream())
+            L.call("nmx_diag_mma_rate", L.i32(N), L.i32(20000), L.i32(slabs), L.i32(ctas), L.ptr(out), L.stream(), L.i32(0))
         torch.cuda.synchronize()
         o = out.cpu().numpy().reshape(-1, 2)[:ctas]
         clk, ns = o[:, 0].mean() / 20000, o[:, 1].mean() / 20000
@@ -41,7 +41,7 @@ if os.environ.get("NMX_CHAIN_DBG", "0") != "0":
         t0 = tr[0, 0, 0, 0, 0]
         g0 = tr[0, 0, 0, 0, 1]
         print(f"--- chain trace save={save} (clocks rel. to start; M* = MMA thread, E* = epilogue warp 2)")
-        print("tile layer |  M:tempty_ok  M:first_issue  M:last_slab_rdy  M:committed |  E:tfull_wake  E:done  | layer period")
+        print("tile layer |  M:tempty_ok  M:full_ok  M:act_ok(issue)  M:committed |  E:wake  E:ld_done  E:h0_arrived  E:layer_done | period")
         prev = None
         for it in range(1, 4):
             for l in range(NLAY):
@@ -49,7 +49,7 @@ if os.environ.get("NMX_CHAIN_DBG", "0") != "0":
                 e = tr[1, it, l, :, 0] - t0
                 per = (m[3] - prev) if prev is not None else 0
                 prev = m[3]
-                print(f"{it:4d} {l:5d} | {m[0]:11d} {m[1]:13d} {m[2]:15d} {m[3]:12d} | {e[0]:12d} {e[2]:8d} | {per:6d}")
+                print(f"{it:4d} {l:5d} | {m[0]:11d} {m[1]:9d} {m[2]:15d} {m[3]:12d} | {e[0]:7d} {e[1]:9d} {e[2]:12d} {e[3]:12d} | {per:6d}")
         dc = tr[0, T - 1, NLAY - 1, 3, 0] - t0
         dg = tr[0, T - 1, NLAY - 1, 3, 1] - g0
         print(f"clock: {dc} clks in {dg} ns -> {dc / dg * 1e3:.0f} MHz; per tile {dc / (T - 1 + 1):.0f} clks")
