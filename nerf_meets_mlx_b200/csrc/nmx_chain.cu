@@ -34,27 +34,35 @@ constexpr int kEpiWarp0 = 0;                // warps 0..15 epilogue (TMEM lane q
 constexpr int kStoreWarp = 16;              // activation-store issuer (training) + TMEM alloc/dealloc
 constexpr int kTmaWarp = 17;
 constexpr int kMmaWarp = 18;
-constexpr int kThreads = 19 * 32;
+constexpr int kMaskWarp = 19;             // backward only: TMA loader of the saved-activation (ReLU mask) chunks
+constexpr int kThreads = 20 * 32;
 constexpr int kStages = 3;
 constexpr int kSlabBytes = 256 * 64 * 2;   // one piece of weights: up to 256 output rows x 64-wide K slab
 constexpr int kChunkBytes = 128 * 64 * 2;  // one 128-row x 64-col bf16 activation chunk
 
-struct Smem {
-  static constexpr int kActOff = 0;                              // 4 chunks (128 x 256 bf16)
-  static constexpr int kX0Off = kActOff + 4 * kChunkBytes;       // pos chunk, dir chunk
-  static constexpr int kRingOff = kX0Off + 2 * kChunkBytes;
-  static constexpr int kBiasOff = kRingOff + kStages * kSlabBytes;       // [kMaxChainLayers][256] fp32
-  static constexpr int kW7Off = kBiasOff + kMaxChainLayers * 256 * 4;    // head-7 weights [8][256] fp32
-  static constexpr int kWrgbOff = kW7Off + 8 * 256 * 4;                  // rgb weights [3][128] fp32
-  static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                // [3][128][4] fp32 partial sums
-  static constexpr int kBarOff = kXchgOff + 3 * 128 * 4 * 4;
+// Shared-memory layout.  Forward: activation tile, resident encoded-input chunks (pos, dir), weight ring, biases and
+// head weights.  Backward: activation tile (dY), FOUR saved-activation (ReLU mask) chunk slots refilled by TMA one
+// layer ahead, weight ring, w_alpha / w_rgb -- exactly 227 KB, so the dynamic shared window must be 1024 B aligned
+// (checked at run time; there is no slack to re-align inside).
+template <int MODE>
+struct SmemT {
+  static constexpr int kActOff = 0;                                       // 4 chunks (128 x 256 bf16)
+  static constexpr int kX0Off = kActOff + 4 * kChunkBytes;                // fwd: pos chunk, dir chunk; bwd: 4 mask slots
+  static constexpr int kRingOff = kX0Off + (MODE == 0 ? 2 : 4) * kChunkBytes;
+  static constexpr int kBiasOff = kRingOff + kStages * kSlabBytes;        // fwd: [kMaxChainLayers][256] fp32
+  static constexpr int kW7Off = kBiasOff + (MODE == 0 ? kMaxChainLayers * 256 * 4 : 0);   // [8][256] / bwd [1][256] fp32
+  static constexpr int kWrgbOff = kW7Off + (MODE == 0 ? 8 : 1) * 256 * 4; // rgb weights [3][128] fp32
+  static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                 // fwd: [3][128][4] fp32 partial sums
+  static constexpr int kBarOff = kXchgOff + (MODE == 0 ? 3 * 128 * 4 * 4 : 0);
   // barriers: full[S], empty[S], tfull[2 stages][2 halves], tempty[2], act_ready[4], x0pos_full, x0pos_empty,
-  //           x0dir_full, x0dir_empty, store_done
-  static constexpr int kNumBars = 2 * kStages + 4 + 2 + 4 + 4 + 1;
+  //           x0dir_full, x0dir_empty, store_done, mask_full[4], mask_empty[4]
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 + 4 + 4 + 1 + 8;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
-  static constexpr int kAlloc = kTotal + 1024;
+  static constexpr int kAlloc = MODE == 0 ? kTotal + 1024 : kTotal;
+  static_assert(kAlloc <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
+using Smem = SmemT<0>;
 
 // NMX_CHAIN_DBG bit 2: CTA 0 records (clock64, globaltimer) at pipeline events of its first kTraceTiles tiles
 constexpr int kTraceTiles = 6;
@@ -91,6 +99,16 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {  // low half <- low
   if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   return d;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 0xFFFF per half whose bf16 value is non-zero (post-ReLU activation > 0)
+__device__ __forceinline__ uint32_t nz_mask_bf16x2(uint32_t v) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+  return __hne2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), z);
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -216,19 +234,67 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
   }
 }
 
+__device__ __forceinline__ uint4 lds128_u(uint32_t addr) {  // ordered (volatile) 16 B shared load
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// backward epilogue of 32 columns: bf16((acc [+ d_sigma * w_alpha]) masked by the saved activation's sign pattern).
+// mask_row_addr: this thread's row inside the TMA-loaded (SW128) chunk of the saved activation.
+template <int EPI>
+__device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
+                                         const uint32_t act_row_addr, const uint32_t swz, const uint32_t mask_row_addr,
+                                         const uint32_t wa_addr, const float ds) {
+  const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
+  const uint64_t ds2 = pack64(__float_as_uint(ds), __float_as_uint(ds));
+#pragma unroll
+  for (int p4 = 0; p4 < 4; ++p4) {
+    const uint32_t piece = (((uint32_t)(sub * 4 + p4)) ^ swz) << 4;
+    float wa[8];
+    if (EPI == 2) {
+      const float4 a0 = lds128(wa_addr + (uint32_t)(c0 + p4 * 8) * 4u);
+      const float4 a1 = lds128(wa_addr + (uint32_t)(c0 + p4 * 8 + 4) * 4u);
+      wa[0] = a0.x; wa[1] = a0.y; wa[2] = a0.z; wa[3] = a0.w; wa[4] = a1.x; wa[5] = a1.y; wa[6] = a1.z; wa[7] = a1.w;
+    }
+    uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+    if (EPI >= 1) m4 = lds128_u(mask_row_addr + piece);
+    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint64_t x = pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]);
+      if (EPI == 2) x = fma_f32x2(ds2, pack64(__float_as_uint(wa[2 * e]), __float_as_uint(wa[2 * e + 1])), x);
+      uint32_t v = cvt_bf16x2<false>(x);
+      if (EPI >= 1) v &= nz_mask_bf16x2(mw[e]);
+      pk[e] = v;
+    }
+    sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
+  }
+  fence_proxy_async_smem();
+}
+
+// MODE 0: forward (bias + ReLU epilogue, heads).  MODE 1: backward data-gradient chain (models/NeRF.py backward of
+// 201-243): step A computes d_hd = (d_rgb W_rgb) * [hd > 0] on the CUDA cores, then every layer is
+// dX = dY W (W^T copies as the K-major B operand), with the ReLU mask of the saved activation (and the alpha head's
+// rank-1 term d_sigma (x) w_alpha on the feature layer) in the epilogue; every dY is TMA-stored for the wgrad kernels.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) {
+mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) {
+  using SL = SmemT<MODE>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // SW128 operand tiles need 1024 B alignment; plain pointer arithmetic keeps the shared address space visible
+  // SW128 operand tiles need 1024 B alignment; plain pointer arithmetic keeps the shared address space visible.
+  // (The backward layout has no slack: there the pad must be 0, which the trap below enforces.)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_act = smem + Smem::kActOff;
-  uint8_t* s_x0 = smem + Smem::kX0Off;
-  uint8_t* s_ring = smem + Smem::kRingOff;
-  float* s_bias = reinterpret_cast<float*>(smem + Smem::kBiasOff);
-  float* s_w7 = reinterpret_cast<float*>(smem + Smem::kW7Off);
-  float* s_wrgb = reinterpret_cast<float*>(smem + Smem::kWrgbOff);
-  float* s_xchg = reinterpret_cast<float*>(smem + Smem::kXchgOff);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Smem::kBarOff);
+  if (MODE == 1 && smem != smem_raw) __trap();
+  uint8_t* s_act = smem + SL::kActOff;
+  uint8_t* s_x0 = smem + SL::kX0Off;
+  uint8_t* s_ring = smem + SL::kRingOff;
+  float* s_bias = reinterpret_cast<float*>(smem + SL::kBiasOff);
+  float* s_w7 = reinterpret_cast<float*>(smem + SL::kW7Off);
+  float* s_wrgb = reinterpret_cast<float*>(smem + SL::kWrgbOff);
+  float* s_xchg = reinterpret_cast<float*>(smem + SL::kXchgOff);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::kBarOff);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;   // [acc stage][half]
   uint64_t* tempty = tfull + 4;
@@ -238,7 +304,9 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   uint64_t* x0dir_full = x0pos_empty + 1;
   uint64_t* x0dir_empty = x0dir_full + 1;
   uint64_t* store_done = x0dir_empty + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::kTmemPtrOff);
+  uint64_t* mask_full = store_done + 1;
+  uint64_t* mask_empty = mask_full + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SL::kTmemPtrOff);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -265,16 +333,22 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     mbar_init(x0dir_full, 1);
     mbar_init(x0dir_empty, 1);
     mbar_init(store_done, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&mask_full[i], 1);
+      mbar_init(&mask_empty[i], kEpiWarps / 2);
+    }
     fence_barrier_init();
   }
   if (warp == kStoreWarp) tmem_alloc<512>(tmem_ptr);
   // stage biases and the register-head weights (fp32) once per CTA
-  for (int i = threadIdx.x; i < NL * 256; i += kThreads) {
-    int l = i >> 8, c = i & 255;
-    s_bias[i] = (c < prm.L[l].N) ? prm.params[prm.L[l].bias_off + c] : 0.0f;
+  if (MODE == 0) {
+    for (int i = threadIdx.x; i < NL * 256; i += kThreads) {
+      int l = i >> 8, c = i & 255;
+      s_bias[i] = (c < prm.L[l].N) ? prm.params[prm.L[l].bias_off + c] : 0.0f;
+    }
   }
   for (int i = threadIdx.x; i < prm.head7_n * 256; i += kThreads) s_w7[i] = prm.params[prm.head7_w_off + i];
-  if (prm.rgb_layer >= 0)
+  if (prm.rgb_layer >= 0 || MODE == 1)
     for (int i = threadIdx.x; i < 3 * 128; i += kThreads) s_wrgb[i] = prm.params[prm.rgb_w_off + i];
   tc_fence_before();
   __syncthreads();
@@ -290,7 +364,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if (it == 0) {
+      if (it == 0 && MODE == 0) {
         if (elect_one()) {
           mbar_arrive_expect_tx(x0pos_full, kChunkBytes);
           tma_load_2d(s_x0, &maps.x0, x0pos_full, 0, tile * 128);
@@ -320,7 +394,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (l == 1 && it > 0 && prm.uses_dir) {
+        if (MODE == 0 && l == 1 && it > 0 && prm.uses_dir) {
           // this tile's view-dir chunk: the previous tile's dir-layer MMAs must have finished reading the buffer
           mbar_wait(x0dir_empty, (uint32_t)((it - 1) & 1));
           if (elect_one()) {
@@ -329,7 +403,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
           }
           __syncwarp();
         }
-        if (l == prm.pos_prefetch_layer) {
+        if (MODE == 0 && l == prm.pos_prefetch_layer) {
           const int ntile = tile + gridDim.x;
           if (ntile < num_tiles) {  // next tile's position chunk, once this tile's last reader (skip layer) is done
             mbar_wait(x0pos_empty, (uint32_t)(it & 1));
@@ -356,6 +430,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     const uint32_t ring16 = smem_u32(s_ring) >> 4;
     constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (MODE == 1) acbits ^= 0x3u;  // step A (d_hd) signals chunks 0,1 before the first layer
       for (int l = 0; l < NL; ++l, ++lcount) {
         const int as = lcount & 1;
         const uint32_t aphase = (lcount >> 1) & 1;
@@ -395,11 +470,13 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) {
-          if (l == prm.pos_last_layer) umma_commit(x0pos_empty);
-          if (l == prm.dir_layer) umma_commit(x0dir_empty);
+        if (MODE == 0) {
+          if (elect_one()) {
+            if (l == prm.pos_last_layer) umma_commit(x0pos_empty);
+            if (l == prm.dir_layer) umma_commit(x0dir_empty);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         trace(tr_on, 0, it, l, 3);
         if (prm.L[l].feeds_next || save) acbits ^= (prm.L[l].N > 128 ? 0xFu : 0x3u);
       }
@@ -409,13 +486,29 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     if (save) {
       uint32_t acbits = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (MODE == 1) {  // step A: d_hd (chunks 0,1) -> its own [P, 128] buffer
+          for (int c = 0; c < 2; ++c) {
+            mbar_wait(&act_ready[c], (acbits >> c) & 1u);
+            if (elect_one() && !(prm.dbg & 16)) {
+              tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
+          acbits ^= 0x3u;
+          if (elect_one()) {
+            tma_store_wait_read<0>();
+            mbar_arrive(store_done);
+          }
+          __syncwarp();
+        }
         for (int l = 0; l < NL; ++l) {
           const int nck = prm.L[l].N / 64;
           const int kind = prm.L[l].save_kind;
           const int row0 = prm.L[l].save_row0 + tile * 128;
           for (int c = 0; c < nck; ++c) {
             mbar_wait(&act_ready[c], (acbits >> c) & 1u);
-            if (elect_one()) {
+            if (elect_one() && !(prm.dbg & 16)) {
               if (kind == 1) tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, row0);
               else if (kind == 2) tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
               tma_store_commit();
@@ -433,6 +526,32 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
     }
+  } else if (warp == kMaskWarp) {
+    // ====================================================== saved-activation (ReLU mask) loader, backward only
+    // Slot c holds column chunk c of the activation that masks the layer being finished; it is refilled with the next
+    // masked step's chunk as soon as the eight epilogue warps that read it have arrived on mask_empty[c].
+    if (MODE == 1 && !(prm.dbg & 8)) {
+      uint32_t fills[4] = {0, 0, 0, 0};
+      auto fill = [&](int c, const CUtensorMap* m, int col, int r0) {
+        if (fills[c] > 0) mbar_wait(&mask_empty[c], (fills[c] - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&mask_full[c], kChunkBytes);
+          tma_load_2d(s_x0 + c * kChunkBytes, m, &mask_full[c], col, r0);
+        }
+        __syncwarp();
+        fills[c]++;
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        fill(0, &maps.w[kMaxChainLayers - 1], 0, tile * 128);   // step A: hd [P, 128]
+        fill(1, &maps.w[kMaxChainLayers - 1], 64, tile * 128);
+        for (int l = 0; l < NL; ++l) {
+          if (prm.L[l].epi < 1) continue;
+          const int r0 = prm.L[l].mask_row0 + tile * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) fill(c, &maps.x0, c * 64, r0);
+        }
+      }
+    }
   } else {
     // ====================================================== epilogue (warps 0..15)
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
@@ -440,97 +559,209 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
     const int row_local = q * 32 + lane;
     const uint32_t swz = (uint32_t)(row_local & 7);
     const uint32_t act_row_addr = smem_u32(s_act) + (uint32_t)row_local * 128u;
-    const uint32_t bias_base = smem_u32(s_bias);
-    const uint32_t w7_addr = smem_u32(s_w7), wrgb_addr = smem_u32(s_wrgb);
-    const bool skip_math = (prm.dbg & 2) != 0;
-    uint32_t lcount = 0;
-    const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
-    const bool vd = prm.rgb_layer >= 0;
-    float hb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // head biases of the view-dir net (rgb, alpha), loaded once
-    if (vd && part == 0) {
-      hb[0] = __ldg(prm.params + prm.rgb_b_off + 0);
-      hb[1] = __ldg(prm.params + prm.rgb_b_off + 1);
-      hb[2] = __ldg(prm.params + prm.rgb_b_off + 2);
-      hb[3] = __ldg(prm.params + prm.head7_b_off);
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int row = tile * 128 + row_local;
-      float hp[8];  // head-7 partial dot products over this thread's columns
-#pragma unroll
-      for (int o = 0; o < 8; ++o) hp[o] = 0.0f;
-      float rgbp[3] = {0.0f, 0.0f, 0.0f};
-      for (int l = 0; l < NL; ++l, ++lcount) {
-        const int as = lcount & 1;
-        const uint32_t aphase = (lcount >> 1) & 1;
-        const int n_halves = prm.L[l].N / 128;
-        const bool signal = prm.L[l].feeds_next || save;
-        // the TMA stores of the previous layer's chunks must have finished reading shared memory
-        if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
-        const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
-        const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
-        uint64_t* tf = &tfull[as * 2];
-        if (l == prm.head7_layer && prm.head7_n == 1)
-          epi_layer<true, 1>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                             w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l);
-        else if (l == prm.head7_layer)
-          epi_layer<true, 3>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                             w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l);
-        else if (l == prm.rgb_layer)
-          epi_layer<true, 2>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                             wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l);
-        else if (prm.L[l].relu)
-          epi_layer<true, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
-                             0, hp, rgbp, skip_math, tr_on, it, l);
-        else
-          epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
-                              0, hp, rgbp, skip_math, tr_on, it, l);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        trace(tr_on, 1, it, l, 3);
+    if constexpr (MODE == 0) {
+      const uint32_t bias_base = smem_u32(s_bias);
+      const uint32_t w7_addr = smem_u32(s_w7), wrgb_addr = smem_u32(s_wrgb);
+      const bool skip_math = (prm.dbg & 2) != 0;
+      uint32_t lcount = 0;
+      const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+      const bool vd = prm.rgb_layer >= 0;
+      float hb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // head biases of the view-dir net (rgb, alpha), loaded once
+      if (vd && part == 0) {
+        hb[0] = __ldg(prm.params + prm.rgb_b_off + 0);
+        hb[1] = __ldg(prm.params + prm.rgb_b_off + 1);
+        hb[2] = __ldg(prm.params + prm.rgb_b_off + 2);
+        hb[3] = __ldg(prm.params + prm.head7_b_off);
       }
-      // ---- register heads: combine the column parts' partial sums (4 values per pass) and write the raw outputs
-      const int nvals = vd ? 4 : prm.head7_n;
-      float tot[8];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) tot[o] = 0.0f;
-      for (int pass = 0; pass * 4 < nvals; ++pass) {
-        float v4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x = 0.0f;
-#pragma unroll
-          for (int o = 0; o < 8; ++o)
-            if (o == pass * 4 + j) x = hp[o];
-          v4[j] = x;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int row = tile * 128 + row_local;
+        float hp[8];  // head-7 partial dot products over this thread's columns
+  #pragma unroll
+        for (int o = 0; o < 8; ++o) hp[o] = 0.0f;
+        float rgbp[3] = {0.0f, 0.0f, 0.0f};
+        for (int l = 0; l < NL; ++l, ++lcount) {
+          const int as = lcount & 1;
+          const uint32_t aphase = (lcount >> 1) & 1;
+          const int n_halves = prm.L[l].N / 128;
+          const bool signal = prm.L[l].feeds_next || save;
+          // the TMA stores of the previous layer's chunks must have finished reading shared memory
+          if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
+          const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
+          const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
+          uint64_t* tf = &tfull[as * 2];
+          if (l == prm.head7_layer && prm.head7_n == 1)
+            epi_layer<true, 1>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                               w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l);
+          else if (l == prm.head7_layer)
+            epi_layer<true, 3>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                               w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l);
+          else if (l == prm.rgb_layer)
+            epi_layer<true, 2>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+                               wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l);
+          else if (prm.L[l].relu)
+            epi_layer<true, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+                               0, hp, rgbp, skip_math, tr_on, it, l);
+          else
+            epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+                                0, hp, rgbp, skip_math, tr_on, it, l);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+          trace(tr_on, 1, it, l, 3);
         }
-        if (vd) { v4[0] = rgbp[0]; v4[1] = rgbp[1]; v4[2] = rgbp[2]; v4[3] = hp[0]; }
-        if (part > 0)
-          *reinterpret_cast<float4*>(s_xchg + ((part - 1) * 128 + row_local) * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        if (part == 0) {
-#pragma unroll
-          for (int pp = 0; pp < 3; ++pp) {
-            const float4 t = *reinterpret_cast<const float4*>(s_xchg + (pp * 128 + row_local) * 4);
-            v4[0] += t.x; v4[1] += t.y; v4[2] += t.z; v4[3] += t.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
+        // ---- register heads: combine the column parts' partial sums (4 values per pass) and write the raw outputs
+        const int nvals = vd ? 4 : prm.head7_n;
+        float tot[8];
+  #pragma unroll
+        for (int o = 0; o < 8; ++o) tot[o] = 0.0f;
+        for (int pass = 0; pass * 4 < nvals; ++pass) {
+          float v4[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x = 0.0f;
+  #pragma unroll
             for (int o = 0; o < 8; ++o)
-              if (o == pass * 4 + j) tot[o] = v4[j];
+              if (o == pass * 4 + j) x = hp[o];
+            v4[j] = x;
+          }
+          if (vd) { v4[0] = rgbp[0]; v4[1] = rgbp[1]; v4[2] = rgbp[2]; v4[3] = hp[0]; }
+          if (part > 0)
+            *reinterpret_cast<float4*>(s_xchg + ((part - 1) * 128 + row_local) * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (part == 0) {
+  #pragma unroll
+            for (int pp = 0; pp < 3; ++pp) {
+              const float4 t = *reinterpret_cast<const float4*>(s_xchg + (pp * 128 + row_local) * 4);
+              v4[0] += t.x; v4[1] += t.y; v4[2] += t.z; v4[3] += t.w;
+            }
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)
+  #pragma unroll
+              for (int o = 0; o < 8; ++o)
+                if (o == pass * 4 + j) tot[o] = v4[j];
+          }
+          if ((pass + 1) * 4 < nvals) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
-        if ((pass + 1) * 4 < nvals) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (part == 0 && row < prm.P) {
+          float* o_row = prm.out + (size_t)row * prm.out_cols;
+          if (vd) {
+            *reinterpret_cast<float4*>(o_row) = make_float4(tot[0] + hb[0], tot[1] + hb[1], tot[2] + hb[2], tot[3] + hb[3]);
+          } else {
+  #pragma unroll
+            for (int o = 0; o < 8; ++o)
+              if (o < prm.head7_n) o_row[o] = tot[o] + __ldg(prm.params + prm.head7_b_off + o);
+          }
+        }
       }
-      if (part == 0 && row < prm.P) {
-        float* o_row = prm.out + (size_t)row * prm.out_cols;
-        if (vd) {
-          *reinterpret_cast<float4*>(o_row) = make_float4(tot[0] + hb[0], tot[1] + hb[1], tot[2] + hb[2], tot[3] + hb[3]);
-        } else {
+  
+    } else {
+      // ---------------------------------------------------- backward data-gradient epilogue
+      const uint32_t wa_addr = smem_u32(s_w7);      // w_alpha [256] fp32
+      const uint32_t wrgb_addr = smem_u32(s_wrgb);  // w_rgb [3][128] fp32
+      const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+      const bool no_mask = (prm.dbg & 8) != 0;  // experiment: skip the saved-activation reads
+      const int c_a = part >> 1, sub_a = part & 1;  // step A: this warp's chunk / 32-column sub-block of d_hd
+      uint32_t lcount = 0, scount = 0;
+      // mask slots this warp reads: c_a (step A / half 0) and 2 + c_a (half 1); u0 / u1 count their uses
+      uint32_t u0 = 0, u1 = 0;
+      const uint32_t mrow0 = smem_u32(s_x0) + (uint32_t)c_a * kChunkBytes + (uint32_t)row_local * 128u;
+      const uint32_t mrow1 = mrow0 + 2u * kChunkBytes;
+      const int col0 = c_a * 64 + sub_a * 32;       // half-0 column of a [P,256] tensor; half 1 = col0 + 128
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int row = tile * 128 + row_local;
+        const bool row_ok = row < prm.P;
+        float4 dr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (row_ok) dr = __ldg(reinterpret_cast<const float4*>(prm.d_out) + row);
+        // ---- step A: d_hd = (d_rgb W_rgb) * [hd > 0]  -> chunks 0,1 (A operand of the dir-layer data gradient)
+        if (scount > 0) mbar_wait(store_done, (scount - 1) & 1);
+        {
+          if (!no_mask) mbar_wait(&mask_full[c_a], u0 & 1);
+          const uint32_t so = act_row_addr + (uint32_t)c_a * kChunkBytes;
 #pragma unroll
-          for (int o = 0; o < 8; ++o)
-            if (o < prm.head7_n) o_row[o] = tot[o] + __ldg(prm.params + prm.head7_b_off + o);
+          for (int p4 = 0; p4 < 4; ++p4) {
+            const int j = part * 32 + p4 * 8;
+            const uint32_t piece = (((uint32_t)(sub_a * 4 + p4)) ^ swz) << 4;
+            float v[8];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float4 w0 = lds128(wrgb_addr + (uint32_t)(0 * 128 + j + hh * 4) * 4u);
+              const float4 w1 = lds128(wrgb_addr + (uint32_t)(1 * 128 + j + hh * 4) * 4u);
+              const float4 w2 = lds128(wrgb_addr + (uint32_t)(2 * 128 + j + hh * 4) * 4u);
+              v[hh * 4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+              v[hh * 4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+              v[hh * 4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+              v[hh * 4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+            }
+            uint4 m4 = make_uint4(~0u, ~0u, ~0u, ~0u);
+            if (!no_mask) m4 = lds128_u(mrow0 + piece);
+            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]) & nz_mask_bf16x2(mw[e]);
+            sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&act_ready[c_a]);
+            if (!no_mask) mbar_arrive(&mask_empty[c_a]);
+          }
+          ++u0;
+        }
+        ++scount;
+        for (int l = 0; l < NL; ++l, ++lcount, ++scount) {
+          const int as = lcount & 1;
+          const uint32_t aphase = (lcount >> 1) & 1;
+          const int epi = no_mask ? (prm.L[l].epi == 2 ? 2 : 0) : prm.L[l].epi;
+          const bool masked = prm.L[l].epi >= 1 && !no_mask;
+          // the TMA stores of the previous step's chunks must have finished reading shared memory
+          mbar_wait(store_done, (scount - 1) & 1);
+          const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
+          // ---- half 0 (chunks 0,1)
+          if (masked) mbar_wait(&mask_full[c_a], u0 & 1);
+          mbar_wait(&tfull[as * 2 + 0], aphase);
+          trace(tr_on, 1, it, l, 0);
+          tc_fence_after();
+          {
+            const int c = c_a;
+            uint32_t r[32];
+            tmem_ld_32x32(tacc + (uint32_t)col0, r);
+            tmem_ld_wait_regs<32>(r);
+            if (epi == 2) bwd_cols<2>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, dr.w);
+            else if (epi == 1) bwd_cols<1>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, 0.0f);
+            else bwd_cols<0>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, 0.0f);
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&act_ready[c]);
+              if (masked) mbar_arrive(&mask_empty[c]);
+            }
+            if (masked) ++u0;
+          }
+          // ---- half 1 (chunks 2,3)
+          if (masked) mbar_wait(&mask_full[2 + c_a], u1 & 1);
+          mbar_wait(&tfull[as * 2 + 1], aphase);
+          tc_fence_after();
+          {
+            const int c = 2 + c_a;
+            uint32_t r[32];
+            tmem_ld_32x32(tacc + (uint32_t)(col0 + 128), r);
+            tmem_ld_wait_regs<32>(r);
+            if (epi == 2) bwd_cols<2>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, dr.w);
+            else if (epi == 1) bwd_cols<1>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, 0.0f);
+            else bwd_cols<0>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, 0.0f);
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&act_ready[c]);
+              if (masked) mbar_arrive(&mask_empty[c]);
+            }
+            if (masked) ++u1;
+          }
+          trace(tr_on, 1, it, l, 2);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
         }
       }
     }
@@ -544,7 +775,8 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
 
 namespace nmx {
 
-int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm_in, cudaStream_t stream) {
+template <int MODE>
+static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaStream_t stream) {
   if (prm_in.P <= 0) return 0;
   ChainParams prm = prm_in;
   for (int l = 0; l < prm.n_layers; ++l) {
@@ -573,14 +805,21 @@ int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm_in, cudaStrea
   }
   static bool attr = false;
   if (!attr) {
-    NMX_CUDA(cudaFuncSetAttribute(mlp_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::kAlloc));
+    NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<MODE>::kAlloc));
     attr = true;
   }
   int tiles = (prm.P + 127) / 128;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  mlp_chain_fwd_kernel<<<grid, kThreads, Smem::kAlloc, stream>>>(maps, prm);
+  mlp_chain_kernel<MODE><<<grid, kThreads, SmemT<MODE>::kAlloc, stream>>>(maps, prm);
   NMX_LAUNCH_CHECK();
   return 0;
+}
+
+int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream) {
+  return launch_chain<0>(maps, prm, stream);
+}
+int launch_chain_bwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream) {
+  return launch_chain<1>(maps, prm, stream);
 }
 
 }  // namespace nmx

@@ -23,6 +23,12 @@ struct ChainLayerDesc {
   int feeds_next;  // its output chunks are the A operand of a later layer (MMA waits on act_ready)
   int save_kind;   // 0 none, 1 = [rows, 256] activation store (h_l / feature), 2 = [P, 128] store (hd)
   int save_row0;   // first row of this layer's region in the activation store
+  // backward chain only: epilogue kind (0 plain, 1 ReLU mask of `mask`, 2 mask + alpha rank-1 term) and the saved
+  // post-ReLU activation [P, mask_ld] bf16 whose sign pattern masks this layer's output
+  int epi;
+  int mask_ld;
+  int mask_row0;   // first row of `mask` inside the activation store (maps.x0 in backward mode), for the L2 prefetch
+  const void* mask;
 };
 
 struct ChainParams {
@@ -36,6 +42,9 @@ struct ChainParams {
   int rgb_layer, rgb_w_off, rgb_b_off;                 // rgb head from the dir layer's output, or rgb_layer = -1
   int uses_dir, x0_dir_col;
   int pos_last_layer, pos_prefetch_layer, dir_layer;
+  // backward chain only: d_raw [P, 4] fp32 (d_rgb, d_sigma) and the saved dir-layer activation hd [P, 128] bf16
+  const float* d_out;
+  const void* hd;
   int dbg;  // experiments only (NMX_CHAIN_DBG): bit 0 = no weight TMA traffic, bit 1 = epilogue math skipped
 };
 
@@ -47,5 +56,6 @@ struct ChainMaps {
 };
 
 int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream);
+int launch_chain_bwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream);
 
 }  // namespace nmx

@@ -56,9 +56,12 @@ bool chain_eligible(const nmx_mlp_plan* p);
 int64_t infer_cap(const nmx_mlp_plan* p) { return chain_eligible(p) ? (int64_t)kNumSMs * 128 * 16 : kInferChunk; }
 
 struct ActLayout {
-  int64_t x0, h0, feat, hd, g0, g1, ghd, dsig, total;
+  int64_t x0, h0, feat, hd, g0, ghd, dsig, total;
   int64_t h_stride;  // bytes between consecutive saved trunk activations (0 = ping-pong of 2 buffers)
+  int64_t g_stride;  // bytes between gradient buffers: 2 ping-pong buffers, or D+1 saved dY slots (fused chain)
 };
+
+bool chain_bwd_eligible(const nmx_mlp_plan* p);
 
 ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   ActLayout a;
@@ -71,10 +74,11 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   off += hbytes * (training ? p->D : 2);
   a.feat = off; off += hbytes;
   a.hd = off; off += x0_only ? 0 : align256(cap * (p->W / 2) * 2);
-  a.g0 = a.g1 = a.ghd = a.dsig = 0;
+  a.g0 = a.ghd = a.dsig = 0;
+  a.g_stride = hbytes;
   if (training) {
-    a.g0 = off; off += hbytes;
-    a.g1 = off; off += hbytes;
+    // fused backward chain: every layer's dY is kept for the wgrad kernels (slots 0..D-1 = dY_l, slot D = d_feature)
+    a.g0 = off; off += hbytes * (chain_bwd_eligible(p) ? p->D + 1 : 2);
     a.ghd = off; off += align256(cap * (p->W / 2) * 2);
   }
   a.total = off;
@@ -526,7 +530,7 @@ struct Ctx {
   bf16* H(int l) const { return (bf16*)(act + al.h0 + al.h_stride * (training ? l : (l & 1))); }
   bf16* FEAT() const { return (bf16*)(act + al.feat); }
   bf16* HD() const { return (bf16*)(act + al.hd); }
-  bf16* G(int i) const { return (bf16*)(act + (i ? al.g1 : al.g0)); }
+  bf16* G(int i) const { return (bf16*)(act + al.g0 + al.g_stride * i); }
   bf16* GHD() const { return (bf16*)(act + al.ghd); }
 };
 
@@ -699,6 +703,69 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   return launch_chain_fwd(maps, prm, c.s);
 }
 
+bool chain_bwd_eligible(const nmx_mlp_plan* p) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("NMX_DISABLE_CHAIN_BWD");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && chain_eligible(p) && p->cfg.use_viewdirs && p->dir_pad == 64;
+}
+
+// Fused data-gradient chain (nmx_chain.cu MODE 1): d_hd -> d_feature -> dY_{D-1} -> ... -> dY_0, every one kept in
+// its G slot for the wgrad kernels.  Layer order: dir-layer dgrad, feature dgrad (+ alpha rank-1, mask h_{D-1}),
+// trunk layers D-1 .. 1 (mask h_{l-1}).
+int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
+  nmx_mlp_plan* p = c.p;
+  const int W = p->W, D = p->D;
+  ChainMaps maps;
+  ChainParams prm;
+  memset(&prm, 0, sizeof(prm));
+  int rc;
+  int nl = 0;
+  {  // d_feature = d_hd . W_dir[:, 0:W]   (K = W/2 over the dir layer's outputs)
+    ChainLayerDesc& d = prm.L[nl];
+    d.src[0] = 0; d.src[1] = 1; d.n_slabs = 2; d.N = W; d.feeds_next = 1; d.epi = 0;
+    d.save_kind = 1; d.save_row0 = (int)(D * cap);
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_dir, W, W / 2, W / 2, 128))) return rc;
+    ++nl;
+  }
+  {  // dY_{D-1} = (d_feature . W_feat + d_sigma (x) w_alpha) * [h_{D-1} > 0]
+    ChainLayerDesc& d = prm.L[nl];
+    for (int k = 0; k < 4; ++k) d.src[k] = k;
+    d.n_slabs = 4; d.N = W; d.feeds_next = 1; d.epi = 2; d.mask = c.H(D - 1); d.mask_ld = W; d.mask_row0 = (int)((D - 1) * cap);
+    d.save_kind = 1; d.save_row0 = (int)((D - 1) * cap);
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_feat, W, W, W, 128))) return rc;
+    ++nl;
+  }
+  for (int l = D - 1; l >= 1; --l, ++nl) {  // dY_{l-1} = (dY_l . W_l[:, h part]) * [h_{l-1} > 0]
+    ChainLayerDesc& d = prm.L[nl];
+    for (int k = 0; k < 4; ++k) d.src[k] = k;
+    d.n_slabs = 4; d.N = W; d.feeds_next = l > 1; d.epi = 1; d.mask = c.H(l - 1); d.mask_ld = W; d.mask_row0 = (int)((l - 1) * cap);
+    d.save_kind = 1; d.save_row0 = (int)((l - 1) * cap);
+    if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_off[l], W, W, W, 128))) return rc;
+  }
+  for (int l = nl; l < kMaxChainLayers; ++l) maps.w[l] = maps.w[0];
+  if (nl >= kMaxChainLayers) { set_error("backward chain: too many layers"); return NMX_E_UNSUPPORTED; }
+  // TMA views of the saved activations (ReLU masks): hd [P, W/2] in the last weight-map slot, h_0..h_{D-1} in maps.x0
+  if ((rc = make_tmap_bf16_2d(&maps.w[kMaxChainLayers - 1], c.HD(), P, W / 2, W / 2, 128))) return rc;
+  prm.n_layers = nl;
+  prm.P = (int)P; prm.save = 1; prm.params = c.params; prm.out = nullptr; prm.out_cols = 4;
+  prm.head7_layer = -1; prm.rgb_layer = -1; prm.head7_n = 1;
+  prm.head7_w_off = (int)p->alpha.w_off; prm.rgb_w_off = (int)p->rgb.w_off;
+  prm.uses_dir = 0; prm.pos_last_layer = -1; prm.pos_prefetch_layer = -1; prm.dir_layer = -1;
+  prm.d_out = d_out; prm.hd = c.HD();
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
+    prm.dbg = dbg & ~3;  // bits 2 (trace), 3 (no mask reads), 4 (no dY stores) apply to the backward chain
+  }
+  if ((rc = make_tmap_bf16_2d(&maps.save, c.G(0), (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&maps.hd, c.GHD(), P, W / 2, W / 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&maps.x0, c.act + c.al.h0, (uint64_t)D * cap, W, W, 128))) return rc;
+  return launch_chain_bwd(maps, prm, c.s);
+}
+
 }  // namespace
 
 extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
@@ -771,6 +838,35 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
     fprintf(stderr, "[nmx] bwd entry sync: %s | ws=%p act=%p params=%p d_out=%p d_params=%p P=%lld HD=%p GHD=%p hl=%p\n",
             cudaGetErrorString(e0), (void*)c.ws, (void*)c.act, (const void*)params, (const void*)d_out, (void*)d_params,
             (long long)P, (void*)c.HD(), (void*)c.GHD(), (const void*)hl);
+  }
+  if (chain_bwd_eligible(p)) {
+    // head weight gradients (their data gradients are produced inside the fused chain)
+    if ((rc = launch_head_bwd(W / 2, 3, c.HD(), W / 2, params + p->rgb.w_off, d_out, out_cols, 0, P,
+                              d_params + p->rgb.w_off, d_params + p->rgb.b_off, nullptr, 0, s))) return rc;
+    if ((rc = launch_head_bwd(W, 1, hl, W, params + p->alpha.w_off, d_out, out_cols, 3, P, d_params + p->alpha.w_off,
+                              d_params + p->alpha.b_off, nullptr, 0, s))) return rc;
+    if ((rc = backward_chain(c, P, p->max_points, d_out))) return rc;
+    // weight gradients from the saved dY slots: dir layer over [feature | dir PE], feature layer, trunk layers
+    float* dWd = d_params + p->dir.w_off;
+    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
+    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
+    if ((rc = wgrad(c.G(p->D), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
+    for (int l = p->D - 1; l >= 0; --l) {
+      const LinearRef& r = p->trunk[l];
+      const bf16* dY = c.G(l);
+      float* dW = d_params + r.w_off;
+      float* db = d_params + r.b_off;
+      const bool skip_in = (r.in == W + p->in_pos);
+      if (l == 0) {
+        if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
+      } else if (skip_in) {
+        if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
+        if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
+      } else {
+        if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
+      }
+    }
+    return 0;
   }
   if (p->cfg.use_viewdirs) {
     // rgb head: d_hd_pre = (d_rgb W_rgb) * [hd > 0]; dW_rgb, db_rgb
