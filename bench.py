@@ -222,7 +222,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
-    # ---- live per-kernel timing of the dominant kernel (layer GEMM) over the same steps
+    # ---- live per-kernel timing (CUDA events on the launching stream, inside libnmx) over the same steps
     peaks, peak_src = load_peaks()
     lib = L.lib()
     import ctypes
@@ -230,10 +230,11 @@ def run_ours(args):
     prof_steps = max(1, min(args.steps, 3))
     for i in range(prof_steps):
         step_resident(i)
-    ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    lib.nmx_profile_report(0, ctypes.byref(ms_k), ctypes.byref(fl_k), ctypes.byref(n_k))
-    ms_w, fl_w, n_w = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    lib.nmx_profile_report(1, ctypes.byref(ms_w), ctypes.byref(fl_w), ctypes.byref(n_w))
+    prof = {}
+    for kind in range(5):
+        ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        lib.nmx_profile_report(kind, ctypes.byref(ms_k), ctypes.byref(fl_k), ctypes.byref(n_k))
+        prof[kind] = (ms_k.value, fl_k.value, n_k.value)
     lib.nmx_profile_enable(0)
 
     # ---- secondary metric: coarse+fine full-frame render (C5), ray tiles sharded over ranks
@@ -264,9 +265,24 @@ def run_ours(args):
         rays_total = B * world
         value = rays_total / (ms_step * 1e-3)
         e2e = rays_total / (ms_e2e * 1e-3)
-        gemm_ms = ms_k.value / max(n_k.value, 1)
-        # algorithmic flops of the layer-GEMM launches = padded flops * (unpadded/padded) ~ report padded separately
-        achieved = fl_k.value / (ms_k.value * 1e-3) / 1e12 if ms_k.value > 0 else 0.0
+        # dominant kernel: the fused MLP chain (forward inference / forward training / backward data gradients);
+        # ALGORITHMIC flops (fwd 593408 MAC/pt, dgrad 557696 MAC/pt) over the measured launch time
+        P_c, P_f = B * N_SAMPLES, B * (N_SAMPLES + N_IMPORTANCE)
+        DGRAD_FLOP_PT = 2 * 557696
+        alg = {2: P_c * FWD_FLOP_PT, 3: (P_c + P_f) * FWD_FLOP_PT, 4: (P_c + P_f) * DGRAD_FLOP_PT}
+        chain_ms = sum(prof[k][0] for k in (2, 3, 4))
+        chain_n = sum(prof[k][2] for k in (2, 3, 4))
+        chain_alg = sum(alg[k] for k in (2, 3, 4)) * prof_steps
+        achieved = chain_alg / (chain_ms * 1e-3) / 1e12 if chain_ms > 0 else 0.0
+        sub = {}
+        for k, name in ((2, "forward_inference"), (3, "forward_training"), (4, "backward_dgrad")):
+            if prof[k][0] > 0:
+                sub[name] = {"tflops": alg[k] * prof_steps / (prof[k][0] * 1e-3) / 1e12, "launches": int(prof[k][2]),
+                             "ms_per_step": prof[k][0] / prof_steps}
+        # wgrad: HBM-bound (reads dY[P,M] and X[P,N] bf16 once per launch)
+        wg_shapes = [(256, 64)] + [(256, 256)] * 7 + [(256, 64)] + [(256, 256)] + [(128, 256), (128, 64)]
+        wg_bytes = sum(2 * (m + n) for m, n in wg_shapes) * (P_c + P_f) * prof_steps
+        wg_ms = prof[1][0]
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -274,7 +290,8 @@ def run_ours(args):
             "config": {"workload": "C3 coarse+fine NeRF training step (reference iteration semantics), 64 stratified + "
                                    "128 importance samples/ray, 8x256 MLPs with view-dir head",
                        "rays_per_gpu": B, "global_rays": rays_total, "parallelism": f"dp{world} ray-sharded",
-                       "l2": "per-step working set (~10 GB of saved activations) >> 126 MB L2; 4 rotating input batches"},
+                       "l2": "per-step working set (~20 GB of saved activations and data gradients) >> 126 MB L2; "
+                             "4 rotating input batches"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "rays/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(B * 9 * 4), "d2h_bytes_per_step": 4},
@@ -283,13 +300,17 @@ def run_ours(args):
                                  "peak_tflops_sustained": peaks["bf16_tflops_sustained"],
                                  "frac": value * FLOP_PER_RAY / 1e12 / world / peaks["bf16_tflops_sustained"],
                                  "flop_per_ray": FLOP_PER_RAY},
-            "roofline": {"bound": "tensor", "kernel": "gemm_kmajor_kernel (layer forward + dgrad GEMMs, tcgen05)",
+            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel (fused whole-MLP forward / backward chains, tcgen05 + TMEM)",
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], "peak_source": peak_src + " sustained (timed inside a long step)",
-                         "launches": int(n_k.value), "avg_launch_ms": gemm_ms, "traffic": None,
-                         "wgrad": {"achieved": (fl_w.value / (ms_w.value * 1e-3) / 1e12) if ms_w.value > 0 else 0.0,
-                                   "launches": int(n_w.value), "total_ms": ms_w.value},
-                         "gemm_total_ms": ms_k.value, "profiled_steps": prof_steps},
+                         "frac": achieved / peaks["bf16_tflops_sustained"],
+                         "peak_source": peak_src + " sustained (timed inside a long step)",
+                         "launches": int(chain_n), "avg_launch_ms": chain_ms / max(chain_n, 1), "traffic": None,
+                         "modes": sub, "profiled_steps": prof_steps,
+                         "wgrad": {"bound": "hbm", "achieved": wg_bytes / (wg_ms * 1e-3) / 1e9 if wg_ms > 0 else 0.0,
+                                   "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": (wg_bytes / (wg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if wg_ms > 0 else 0.0,
+                                   "tflops": (prof[1][1] / (wg_ms * 1e-3) / 1e12) if wg_ms > 0 else 0.0,
+                                   "launches": int(prof[1][2]), "ms_per_step": wg_ms / prof_steps}},
             "render": render,
         }
         if not args.no_cpu_baseline and world >= 1:

@@ -153,7 +153,9 @@ int nmx_wgrad_bf16(const void* dY, const void* X, float* dW, float* db, int64_t 
 int nmx_colsum_bf16(const void* Y, float* out, int64_t P, int N, void* stream);
 
 /* live per-kernel timing for bench.py's roofline: when enabled, every tensor-core GEMM launch is bracketed by CUDA
- * events on its own stream.  kind 0 = layer GEMM (forward + dgrad), 1 = wgrad.  flops are the PADDED flops launched. */
+ * events on its own stream.  kind 0 = layer GEMM (forward + dgrad of nets the fused chain does not cover), 1 = wgrad,
+ * 2 = fused chain forward (inference), 3 = fused chain forward (training: saves activations), 4 = fused chain backward
+ * (data gradients).  flops are the PADDED flops launched. */
 int nmx_profile_enable(int on);
 int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t* launches);
 

@@ -20,6 +20,7 @@
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
 #include "nmx_chain.cuh"
+#include "nmx_gemm.cuh"
 
 using namespace nmx;
 using namespace nmx::sm100;
@@ -810,7 +811,11 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaSt
   }
   int tiles = (prm.P + 127) / 128;
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  double flops = 0.0;  // padded flops actually issued to the tensor pipe
+  for (int l = 0; l < prm.n_layers; ++l) flops += 2.0 * prm.P * prm.L[l].N * 64.0 * prm.L[l].n_slabs;
+  prof_begin(MODE == 1 ? 4 : (prm.save ? 3 : 2), flops, stream);
   mlp_chain_kernel<MODE><<<grid, kThreads, SmemT<MODE>::kAlloc, stream>>>(maps, prm);
+  prof_end(stream);
   NMX_LAUNCH_CHECK();
   return 0;
 }

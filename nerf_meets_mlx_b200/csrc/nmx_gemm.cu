@@ -496,14 +496,14 @@ namespace nmx {
 struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
-static void prof_begin(int kind, double flops, cudaStream_t s) {
+void prof_begin(int kind, double flops, cudaStream_t s) {
   if (!g_prof_on) return;
   ProfRec r; r.kind = kind; r.flops = flops;
   cudaEventCreate(&r.a); cudaEventCreate(&r.b);
   cudaEventRecord(r.a, s);
   g_prof.push_back(r);
 }
-static void prof_end(cudaStream_t s) {
+void prof_end(cudaStream_t s) {
   if (!g_prof_on) return;
   cudaEventRecord(g_prof.back().b, s);
 }

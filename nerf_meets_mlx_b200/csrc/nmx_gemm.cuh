@@ -26,6 +26,11 @@ struct WgradDesc {
   float* db;                                          // optional: db[m] += sum_p dY[p, m] (bias gradient), or null
 };
 
+// live profiling hooks (nmx_profile_enable): kind 0 layer GEMM, 1 wgrad, 2 chain forward (inference), 3 chain forward
+// (training, saves activations), 4 chain backward (data gradients)
+void prof_begin(int kind, double flops, cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 int launch_wgrad(const WgradDesc& g, cudaStream_t stream);
 int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out, cudaStream_t stream);
