@@ -167,6 +167,9 @@ int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t*
  * variable NMX_CHAIN_DBG has bit 2 set. */
 int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream, int mode);
 int nmx_chain_trace_read(long long* out, int n);
+/* byte offsets of the training workspace regions: out[12] = {activation base, x0, h0, h stride, feature, hd, g0, g stride,
+ * ghd, relu sign bits, capacity (points), x0 columns}; region offsets are relative to the activation base. */
+int nmx_mlp_debug_layout(const nmx_mlp_plan* plan, int64_t* out, int n);
 
 #ifdef __cplusplus
 }

@@ -40,27 +40,28 @@ constexpr int kThreads = 20 * 32;
 constexpr int kStages = 3;
 constexpr int kSlabBytes = 256 * 64 * 2;   // one piece of weights: up to 256 output rows x 64-wide K slab
 constexpr int kChunkBytes = 128 * 64 * 2;  // one 128-row x 64-col bf16 activation chunk
+constexpr int kBitsBytes = 128 * 32;       // ReLU sign bits of one 128-row x 256-col activation tile
 
 // Shared-memory layout.  Forward: activation tile, resident encoded-input chunks (pos, dir), weight ring, biases and
-// head weights.  Backward: activation tile (dY), FOUR saved-activation (ReLU mask) chunk slots refilled by TMA one
-// layer ahead, weight ring, w_alpha / w_rgb -- exactly 227 KB, so the dynamic shared window must be 1024 B aligned
-// (checked at run time; there is no slack to re-align inside).
+// head weights (+ a 4 KB ReLU sign-bit staging tile aliased onto rows 1..4 of the head-7 weight block, which a
+// view-dir net does not use).  Backward: activation tile (dY), two 4 KB sign-bit slots refilled by bulk copies one
+// step ahead, weight ring, w_alpha / w_rgb.
 template <int MODE>
 struct SmemT {
   static constexpr int kActOff = 0;                                       // 4 chunks (128 x 256 bf16)
-  static constexpr int kX0Off = kActOff + 4 * kChunkBytes;                // fwd: pos chunk, dir chunk; bwd: 4 mask slots
-  static constexpr int kRingOff = kX0Off + (MODE == 0 ? 2 : 4) * kChunkBytes;
+  static constexpr int kX0Off = kActOff + 4 * kChunkBytes;                // fwd: pos chunk, dir chunk; bwd: 2 sign-bit slots
+  static constexpr int kRingOff = kX0Off + (MODE == 0 ? 2 * kChunkBytes : 2 * kBitsBytes);
   static constexpr int kBiasOff = kRingOff + kStages * kSlabBytes;        // fwd: [kMaxChainLayers][256] fp32
   static constexpr int kW7Off = kBiasOff + (MODE == 0 ? kMaxChainLayers * 256 * 4 : 0);   // [8][256] / bwd [1][256] fp32
   static constexpr int kWrgbOff = kW7Off + (MODE == 0 ? 8 : 1) * 256 * 4; // rgb weights [3][128] fp32
   static constexpr int kXchgOff = kWrgbOff + 3 * 128 * 4;                 // fwd: [3][128][4] fp32 partial sums
   static constexpr int kBarOff = kXchgOff + (MODE == 0 ? 3 * 128 * 4 * 4 : 0);
   // barriers: full[S], empty[S], tfull[2 stages][2 halves], tempty[2], act_ready[4], x0pos_full, x0pos_empty,
-  //           x0dir_full, x0dir_empty, store_done, mask_full[4], mask_empty[4]
-  static constexpr int kNumBars = 2 * kStages + 4 + 2 + 4 + 4 + 1 + 8;
+  //           x0dir_full, x0dir_empty, store_done, bits_full[2], bits_empty[2]
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 + 4 + 4 + 1 + 4;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
-  static constexpr int kAlloc = MODE == 0 ? kTotal + 1024 : kTotal;
+  static constexpr int kAlloc = kTotal + 1024;
   static_assert(kAlloc <= 232448, "exceeds the 227 KB shared-memory limit of sm_100");
 };
 using Smem = SmemT<0>;
@@ -155,8 +156,10 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
 template <bool RELU, int HEAD>
 __device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
                                          const uint32_t bias_addr, const uint32_t act_row_addr, const uint32_t swz,
-                                         const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3]) {
+                                         const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3],
+                                         const uint32_t bits_addr) {
   const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
+  uint32_t bits = 0;  // ReLU sign bits of this thread's 32 columns (bit e / 16+e = columns 2e / 2e+1)
 #pragma unroll
   for (int p4 = 0; p4 < 4; ++p4) {
     const float4 b0 = lds128(bias_addr + (uint32_t)(c0 + p4 * 8) * 4u);
@@ -168,6 +171,7 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, c
       const uint64_t x = add_f32x2(pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]),
                                    pack64(__float_as_uint(bv[2 * e]), __float_as_uint(bv[2 * e + 1])));
       pk[e] = cvt_bf16x2<RELU>(x);
+      if (RELU) bits |= nz_mask_bf16x2(pk[e]) & (0x00010001u << (p4 * 4 + e));
     }
     sts128(so + ((((uint32_t)(sub * 4 + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
     if (HEAD != 0) {
@@ -199,6 +203,7 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, c
       }
     }
   }
+  if (RELU && bits_addr != 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(bits_addr), "r"(bits) : "memory");
   fence_proxy_async_smem();
 }
 
@@ -211,7 +216,8 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
                                           const int part, const uint32_t bias_addr, const uint32_t act_row_addr,
                                           const uint32_t swz, uint64_t* act_ready, const bool signal, const int lane,
                                           const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3],
-                                          const bool skip_math, const bool tr_on, const int it, const int l) {
+                                          const bool skip_math, const bool tr_on, const int it, const int l,
+                                          const uint32_t bits_row_addr) {
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     mbar_wait(&tfull2[h], aphase);
@@ -226,7 +232,8 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
         tmem_ld_32x32(tacc + (uint32_t)c0, r);
         tmem_ld_wait_regs<32>(r);
         if (h == 0) trace(tr_on, 1, it, l, 1);
-        epi_cols<RELU, HEAD>(r, c, c0, sub, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp);
+        epi_cols<RELU, HEAD>(r, c, c0, sub, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp,
+                             bits_row_addr ? bits_row_addr + (uint32_t)(4 * h + part) * 4u : 0u);
       }
       __syncwarp();
       if (signal && lane == 0) mbar_arrive(&act_ready[c]);
@@ -235,17 +242,11 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
   }
 }
 
-__device__ __forceinline__ uint4 lds128_u(uint32_t addr) {  // ordered (volatile) 16 B shared load
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
-// backward epilogue of 32 columns: bf16((acc [+ d_sigma * w_alpha]) masked by the saved activation's sign pattern).
-// mask_row_addr: this thread's row inside the TMA-loaded (SW128) chunk of the saved activation.
+// backward epilogue of 32 columns: bf16((acc [+ d_sigma * w_alpha]) masked by the ReLU sign bits of the saved
+// activation (`bits`: bit e / 16+e = columns 2e / 2e+1 of this thread's 32 columns)).
 template <int EPI>
 __device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
-                                         const uint32_t act_row_addr, const uint32_t swz, const uint32_t mask_row_addr,
+                                         const uint32_t act_row_addr, const uint32_t swz, const uint32_t bits,
                                          const uint32_t wa_addr, const float ds) {
   const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
   const uint64_t ds2 = pack64(__float_as_uint(ds), __float_as_uint(ds));
@@ -258,16 +259,13 @@ __device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, c
       const float4 a1 = lds128(wa_addr + (uint32_t)(c0 + p4 * 8 + 4) * 4u);
       wa[0] = a0.x; wa[1] = a0.y; wa[2] = a0.z; wa[3] = a0.w; wa[4] = a1.x; wa[5] = a1.y; wa[6] = a1.z; wa[7] = a1.w;
     }
-    uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
-    if (EPI >= 1) m4 = lds128_u(mask_row_addr + piece);
-    const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
     uint32_t pk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       uint64_t x = pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]);
       if (EPI == 2) x = fma_f32x2(ds2, pack64(__float_as_uint(wa[2 * e]), __float_as_uint(wa[2 * e + 1])), x);
       uint32_t v = cvt_bf16x2<false>(x);
-      if (EPI >= 1) v &= nz_mask_bf16x2(mw[e]);
+      if (EPI >= 1) v &= ((bits >> (p4 * 4 + e)) & 0x00010001u) * 0xFFFFu;
       pk[e] = v;
     }
     sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
@@ -287,7 +285,6 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
   // SW128 operand tiles need 1024 B alignment; plain pointer arithmetic keeps the shared address space visible.
   // (The backward layout has no slack: there the pad must be 0, which the trap below enforces.)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  if (MODE == 1 && smem != smem_raw) __trap();
   uint8_t* s_act = smem + SL::kActOff;
   uint8_t* s_x0 = smem + SL::kX0Off;
   uint8_t* s_ring = smem + SL::kRingOff;
@@ -305,8 +302,10 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
   uint64_t* x0dir_full = x0pos_empty + 1;
   uint64_t* x0dir_empty = x0dir_full + 1;
   uint64_t* store_done = x0dir_empty + 1;
-  uint64_t* mask_full = store_done + 1;
-  uint64_t* mask_empty = mask_full + 4;
+  uint64_t* bits_full = store_done + 1;
+  uint64_t* bits_empty = bits_full + 2;
+  // forward: sign-bit staging tile (rows 1..4 of the head-7 weight block); backward: slot 0 of the two bit slots
+  uint32_t* s_bits = MODE == 0 ? reinterpret_cast<uint32_t*>(s_w7 + 256) : reinterpret_cast<uint32_t*>(s_x0);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + SL::kTmemPtrOff);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
@@ -334,9 +333,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     mbar_init(x0dir_full, 1);
     mbar_init(x0dir_empty, 1);
     mbar_init(store_done, 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&mask_full[i], 1);
-      mbar_init(&mask_empty[i], kEpiWarps / 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bits_full[i], 1);
+      mbar_init(&bits_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -517,6 +516,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
             __syncwarp();
           }
           acbits ^= (nck == 4 ? 0xFu : 0x3u);
+          if (MODE == 0 && prm.bits != nullptr && prm.L[l].bits_row0 >= 0) {
+            if (elect_one() && !(prm.dbg & 16)) {  // the layer's ReLU sign bits: one contiguous 4 KB tile
+              bulk_store_1d(prm.bits + ((size_t)prm.L[l].bits_row0 + (size_t)tile * 128) * 8, s_bits, kBitsBytes);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
           if (elect_one()) {
             tma_store_wait_read<0>();  // the epilogue of the next layer may overwrite the chunks
             mbar_arrive(store_done);
@@ -528,29 +534,26 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       __syncwarp();
     }
   } else if (warp == kMaskWarp) {
-    // ====================================================== saved-activation (ReLU mask) loader, backward only
-    // Slot c holds column chunk c of the activation that masks the layer being finished; it is refilled with the next
-    // masked step's chunk as soon as the eight epilogue warps that read it have arrived on mask_empty[c].
+    // ====================================================== ReLU sign-bit loader, backward only
+    // Masked step s (step A, then every masked layer) reads slot s & 1: a contiguous 4 KB tile of sign bits, bulk-copied
+    // one step ahead; a slot is refilled once all sixteen epilogue warps have arrived on bits_empty.
     if (MODE == 1 && !(prm.dbg & 8)) {
-      uint32_t fills[4] = {0, 0, 0, 0};
-      auto fill = [&](int c, const CUtensorMap* m, int col, int r0) {
-        if (fills[c] > 0) mbar_wait(&mask_empty[c], (fills[c] - 1) & 1);
+      uint32_t step = 0;
+      auto fill = [&](int row0) {
+        const uint32_t slot = step & 1u;
+        if (step >= 2) mbar_wait(&bits_empty[slot], ((step >> 1) - 1) & 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&mask_full[c], kChunkBytes);
-          tma_load_2d(s_x0 + c * kChunkBytes, m, &mask_full[c], col, r0);
+          mbar_arrive_expect_tx(&bits_full[slot], kBitsBytes);
+          bulk_load_1d(reinterpret_cast<uint8_t*>(s_bits) + slot * kBitsBytes, prm.bits + (size_t)row0 * 8, kBitsBytes,
+                       &bits_full[slot]);
         }
         __syncwarp();
-        fills[c]++;
+        ++step;
       };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        fill(0, &maps.w[kMaxChainLayers - 1], 0, tile * 128);   // step A: hd [P, 128]
-        fill(1, &maps.w[kMaxChainLayers - 1], 64, tile * 128);
-        for (int l = 0; l < NL; ++l) {
-          if (prm.L[l].epi < 1) continue;
-          const int r0 = prm.L[l].mask_row0 + tile * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) fill(c, &maps.x0, c * 64, r0);
-        }
+        fill(prm.hd_bits_row0 + tile * 128);  // step A
+        for (int l = 0; l < NL; ++l)
+          if (prm.L[l].epi >= 1) fill(prm.L[l].bits_row0 + tile * 128);
       }
     }
   } else {
@@ -590,22 +593,25 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
           const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
           const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
+          // sign-bit staging row of this thread (training forward of a net whose backward is the fused chain)
+          const uint32_t bra = (save && prm.bits != nullptr && prm.L[l].bits_row0 >= 0)
+                                   ? smem_u32(s_bits) + (uint32_t)row_local * 32u : 0u;
           uint64_t* tf = &tfull[as * 2];
           if (l == prm.head7_layer && prm.head7_n == 1)
             epi_layer<true, 1>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                               w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l);
+                               w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (l == prm.head7_layer)
             epi_layer<true, 3>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                               w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l);
+                               w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (l == prm.rgb_layer)
             epi_layer<true, 2>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
-                               wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l);
+                               wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (prm.L[l].relu)
             epi_layer<true, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
-                               0, hp, rgbp, skip_math, tr_on, it, l);
+                               0, hp, rgbp, skip_math, tr_on, it, l, bra);
           else
             epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
-                                0, hp, rgbp, skip_math, tr_on, it, l);
+                                0, hp, rgbp, skip_math, tr_on, it, l, bra);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[as]);
@@ -664,11 +670,14 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       const bool no_mask = (prm.dbg & 8) != 0;  // experiment: skip the saved-activation reads
       const int c_a = part >> 1, sub_a = part & 1;  // step A: this warp's chunk / 32-column sub-block of d_hd
       uint32_t lcount = 0, scount = 0;
-      // mask slots this warp reads: c_a (step A / half 0) and 2 + c_a (half 1); u0 / u1 count their uses
-      uint32_t u0 = 0, u1 = 0;
-      const uint32_t mrow0 = smem_u32(s_x0) + (uint32_t)c_a * kChunkBytes + (uint32_t)row_local * 128u;
-      const uint32_t mrow1 = mrow0 + 2u * kChunkBytes;
+      uint32_t mstep = 0;  // masked steps so far (step A + masked layers): slot = mstep & 1, parity = (mstep >> 1) & 1
+      const uint32_t bits_base = smem_u32(s_bits) + (uint32_t)row_local * 32u;
       const int col0 = c_a * 64 + sub_a * 32;       // half-0 column of a [P,256] tensor; half 1 = col0 + 128
+      auto ld_bits = [&](uint32_t slot, int w) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bits_base + slot * kBitsBytes + (uint32_t)w * 4u) : "memory");
+        return v;
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int row = tile * 128 + row_local;
@@ -678,7 +687,11 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
         // ---- step A: d_hd = (d_rgb W_rgb) * [hd > 0]  -> chunks 0,1 (A operand of the dir-layer data gradient)
         if (scount > 0) mbar_wait(store_done, (scount - 1) & 1);
         {
-          if (!no_mask) mbar_wait(&mask_full[c_a], u0 & 1);
+          uint32_t bits = ~0u;
+          if (!no_mask) {
+            mbar_wait(&bits_full[mstep & 1u], (mstep >> 1) & 1u);
+            bits = ld_bits(mstep & 1u, part);
+          }
           const uint32_t so = act_row_addr + (uint32_t)c_a * kChunkBytes;
 #pragma unroll
           for (int p4 = 0; p4 < 4; ++p4) {
@@ -695,21 +708,19 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
               v[hh * 4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
               v[hh * 4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
             }
-            uint4 m4 = make_uint4(~0u, ~0u, ~0u, ~0u);
-            if (!no_mask) m4 = lds128_u(mrow0 + piece);
-            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
             uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]) & nz_mask_bf16x2(mw[e]);
+            for (int e = 0; e < 4; ++e)
+              pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]) & (((bits >> (p4 * 4 + e)) & 0x00010001u) * 0xFFFFu);
             sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&act_ready[c_a]);
-            if (!no_mask) mbar_arrive(&mask_empty[c_a]);
+            if (!no_mask) mbar_arrive(&bits_empty[mstep & 1u]);
           }
-          ++u0;
+          if (!no_mask) ++mstep;
         }
         ++scount;
         for (int l = 0; l < NL; ++l, ++lcount, ++scount) {
@@ -717,11 +728,18 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           const uint32_t aphase = (lcount >> 1) & 1;
           const int epi = no_mask ? (prm.L[l].epi == 2 ? 2 : 0) : prm.L[l].epi;
           const bool masked = prm.L[l].epi >= 1 && !no_mask;
+          const uint32_t slot = mstep & 1u;
           // the TMA stores of the previous step's chunks must have finished reading shared memory
           mbar_wait(store_done, (scount - 1) & 1);
           const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
+          uint32_t bits0 = 0, bits1 = 0;
+          if (masked) {
+            mbar_wait(&bits_full[slot], (mstep >> 1) & 1u);
+            bits0 = ld_bits(slot, part);
+            bits1 = ld_bits(slot, 4 + part);
+            ++mstep;
+          }
           // ---- half 0 (chunks 0,1)
-          if (masked) mbar_wait(&mask_full[c_a], u0 & 1);
           mbar_wait(&tfull[as * 2 + 0], aphase);
           trace(tr_on, 1, it, l, 0);
           tc_fence_after();
@@ -730,18 +748,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
             uint32_t r[32];
             tmem_ld_32x32(tacc + (uint32_t)col0, r);
             tmem_ld_wait_regs<32>(r);
-            if (epi == 2) bwd_cols<2>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, dr.w);
-            else if (epi == 1) bwd_cols<1>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, 0.0f);
-            else bwd_cols<0>(r, c, col0, sub_a, act_row_addr, swz, mrow0, wa_addr, 0.0f);
+            if (epi == 2) bwd_cols<2>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, dr.w);
+            else if (epi == 1) bwd_cols<1>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, 0.0f);
+            else bwd_cols<0>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, 0.0f);
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&act_ready[c]);
-              if (masked) mbar_arrive(&mask_empty[c]);
-            }
-            if (masked) ++u0;
+            if (lane == 0) mbar_arrive(&act_ready[c]);
           }
           // ---- half 1 (chunks 2,3)
-          if (masked) mbar_wait(&mask_full[2 + c_a], u1 & 1);
           mbar_wait(&tfull[as * 2 + 1], aphase);
           tc_fence_after();
           {
@@ -749,15 +762,14 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
             uint32_t r[32];
             tmem_ld_32x32(tacc + (uint32_t)(col0 + 128), r);
             tmem_ld_wait_regs<32>(r);
-            if (epi == 2) bwd_cols<2>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, dr.w);
-            else if (epi == 1) bwd_cols<1>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, 0.0f);
-            else bwd_cols<0>(r, c, col0 + 128, sub_a, act_row_addr, swz, mrow1, wa_addr, 0.0f);
+            if (epi == 2) bwd_cols<2>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, dr.w);
+            else if (epi == 1) bwd_cols<1>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, 0.0f);
+            else bwd_cols<0>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, 0.0f);
             __syncwarp();
             if (lane == 0) {
               mbar_arrive(&act_ready[c]);
-              if (masked) mbar_arrive(&mask_empty[c]);
+              if (masked) mbar_arrive(&bits_empty[slot]);  // the slot can be refilled
             }
-            if (masked) ++u1;
           }
           trace(tr_on, 1, it, l, 2);
           tc_fence_before();

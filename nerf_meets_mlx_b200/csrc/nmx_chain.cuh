@@ -23,12 +23,12 @@ struct ChainLayerDesc {
   int feeds_next;  // its output chunks are the A operand of a later layer (MMA waits on act_ready)
   int save_kind;   // 0 none, 1 = [rows, 256] activation store (h_l / feature), 2 = [P, 128] store (hd)
   int save_row0;   // first row of this layer's region in the activation store
-  // backward chain only: epilogue kind (0 plain, 1 ReLU mask of `mask`, 2 mask + alpha rank-1 term) and the saved
-  // post-ReLU activation [P, mask_ld] bf16 whose sign pattern masks this layer's output
+  // ReLU sign bits (1 bit per activation, 32 B per point and layer: bit e / 16+e of word w = columns 32w+2e / 32w+2e+1).
+  // forward (training): row offset of this layer's slot in ChainParams::bits, or -1 (layer has no ReLU / not saved);
+  // backward: slot of the activation that masks this layer's output (epi >= 1)
+  int bits_row0;
+  // backward chain only: epilogue kind (0 plain, 1 ReLU mask, 2 mask + alpha rank-1 term)
   int epi;
-  int mask_ld;
-  int mask_row0;   // first row of `mask` inside the activation store (maps.x0 in backward mode), for the L2 prefetch
-  const void* mask;
 };
 
 struct ChainParams {
@@ -42,9 +42,11 @@ struct ChainParams {
   int rgb_layer, rgb_w_off, rgb_b_off;                 // rgb head from the dir layer's output, or rgb_layer = -1
   int uses_dir, x0_dir_col;
   int pos_last_layer, pos_prefetch_layer, dir_layer;
-  // backward chain only: d_raw [P, 4] fp32 (d_rgb, d_sigma) and the saved dir-layer activation hd [P, 128] bf16
+  // ReLU sign-bit store [slots * cap rows][8] uint32: written by the training forward, read by the backward chain
+  uint32_t* bits;
+  int hd_bits_row0;   // backward: slot of the dir-layer activation hd (masks step A)
+  // backward chain only: d_raw [P, 4] fp32 (d_rgb, d_sigma)
   const float* d_out;
-  const void* hd;
   int dbg;  // experiments only (NMX_CHAIN_DBG): bit 0 = no weight TMA traffic, bit 1 = epilogue math skipped
 };
 

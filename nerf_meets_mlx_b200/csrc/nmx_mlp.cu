@@ -56,7 +56,7 @@ bool chain_eligible(const nmx_mlp_plan* p);
 int64_t infer_cap(const nmx_mlp_plan* p) { return chain_eligible(p) ? (int64_t)kNumSMs * 128 * 16 : kInferChunk; }
 
 struct ActLayout {
-  int64_t x0, h0, feat, hd, g0, ghd, dsig, total;
+  int64_t x0, h0, feat, hd, g0, ghd, bits, dsig, total;
   int64_t h_stride;  // bytes between consecutive saved trunk activations (0 = ping-pong of 2 buffers)
   int64_t g_stride;  // bytes between gradient buffers: 2 ping-pong buffers, or D+1 saved dY slots (fused chain)
 };
@@ -74,12 +74,14 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   off += hbytes * (training ? p->D : 2);
   a.feat = off; off += hbytes;
   a.hd = off; off += x0_only ? 0 : align256(cap * (p->W / 2) * 2);
-  a.g0 = a.ghd = a.dsig = 0;
+  a.g0 = a.ghd = a.bits = a.dsig = 0;
   a.g_stride = hbytes;
   if (training) {
     // fused backward chain: every layer's dY is kept for the wgrad kernels (slots 0..D-1 = dY_l, slot D = d_feature)
     a.g0 = off; off += hbytes * (chain_bwd_eligible(p) ? p->D + 1 : 2);
     a.ghd = off; off += align256(cap * (p->W / 2) * 2);
+    // ReLU sign bits (32 B per point and slot): slots 0..D-1 = h_l, slot D = hd
+    a.bits = off; if (chain_bwd_eligible(p)) off += align256(cap * 32) * (p->D + 1);
   }
   a.total = off;
   return a;
@@ -649,6 +651,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
       if (skip_in) { d.src[ns++] = kSrcPos; prm.pos_last_layer = nl; }
       for (int k = 0; k < 4; ++k) d.src[ns++] = k;
     }
+    d.bits_row0 = (int)(l * cap);
     d.n_slabs = ns; d.N = W; d.relu = 1; d.bias_off = (int)p->trunk[l].b_off;
     d.feeds_next = (l < D - 1) || p->cfg.use_viewdirs;
     d.save_kind = c.training ? 1 : 0; d.save_row0 = (int)(l * cap);
@@ -659,6 +662,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   if (p->cfg.use_viewdirs) {
     ChainLayerDesc& f = prm.L[nl];
     for (int k = 0; k < 4; ++k) f.src[k] = k;
+    f.bits_row0 = -1;
     f.n_slabs = 4; f.N = W; f.relu = 0; f.bias_off = (int)p->feat.b_off; f.feeds_next = 1;
     f.save_kind = c.training ? 1 : 0; f.save_row0 = (int)(D * cap);
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_feat, W, W, W, 128))) return rc;
@@ -666,6 +670,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
     ChainLayerDesc& d = prm.L[nl];
     for (int k = 0; k < 4; ++k) d.src[k] = k;
     d.src[4] = kSrcDir;
+    d.bits_row0 = (int)(D * cap);
     d.n_slabs = 5; d.N = W / 2; d.relu = 1; d.bias_off = (int)p->dir.b_off; d.feeds_next = 0;
     d.save_kind = c.training ? 2 : 0; d.save_row0 = 0;
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_dir, W / 2, p->wf_dir_k, p->wf_dir_k, 128))) return rc;
@@ -687,6 +692,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
     if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
     prm.dbg = dbg;
   }
+  prm.bits = (c.training && chain_bwd_eligible(p)) ? (uint32_t*)(c.act + c.al.bits) : nullptr;
   prm.P = (int)npts; prm.save = c.training ? 1 : 0; prm.params = c.params; prm.out = out; prm.out_cols = out_cols;
   if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
   if (c.training) {
@@ -733,7 +739,7 @@ int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
   {  // dY_{D-1} = (d_feature . W_feat + d_sigma (x) w_alpha) * [h_{D-1} > 0]
     ChainLayerDesc& d = prm.L[nl];
     for (int k = 0; k < 4; ++k) d.src[k] = k;
-    d.n_slabs = 4; d.N = W; d.feeds_next = 1; d.epi = 2; d.mask = c.H(D - 1); d.mask_ld = W; d.mask_row0 = (int)((D - 1) * cap);
+    d.n_slabs = 4; d.N = W; d.feeds_next = 1; d.epi = 2; d.bits_row0 = (int)((D - 1) * cap);
     d.save_kind = 1; d.save_row0 = (int)((D - 1) * cap);
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_feat, W, W, W, 128))) return rc;
     ++nl;
@@ -741,20 +747,18 @@ int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
   for (int l = D - 1; l >= 1; --l, ++nl) {  // dY_{l-1} = (dY_l . W_l[:, h part]) * [h_{l-1} > 0]
     ChainLayerDesc& d = prm.L[nl];
     for (int k = 0; k < 4; ++k) d.src[k] = k;
-    d.n_slabs = 4; d.N = W; d.feeds_next = l > 1; d.epi = 1; d.mask = c.H(l - 1); d.mask_ld = W; d.mask_row0 = (int)((l - 1) * cap);
+    d.n_slabs = 4; d.N = W; d.feeds_next = l > 1; d.epi = 1; d.bits_row0 = (int)((l - 1) * cap);
     d.save_kind = 1; d.save_row0 = (int)((l - 1) * cap);
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_off[l], W, W, W, 128))) return rc;
   }
   for (int l = nl; l < kMaxChainLayers; ++l) maps.w[l] = maps.w[0];
   if (nl >= kMaxChainLayers) { set_error("backward chain: too many layers"); return NMX_E_UNSUPPORTED; }
-  // TMA views of the saved activations (ReLU masks): hd [P, W/2] in the last weight-map slot, h_0..h_{D-1} in maps.x0
-  if ((rc = make_tmap_bf16_2d(&maps.w[kMaxChainLayers - 1], c.HD(), P, W / 2, W / 2, 128))) return rc;
   prm.n_layers = nl;
   prm.P = (int)P; prm.save = 1; prm.params = c.params; prm.out = nullptr; prm.out_cols = 4;
   prm.head7_layer = -1; prm.rgb_layer = -1; prm.head7_n = 1;
   prm.head7_w_off = (int)p->alpha.w_off; prm.rgb_w_off = (int)p->rgb.w_off;
   prm.uses_dir = 0; prm.pos_last_layer = -1; prm.pos_prefetch_layer = -1; prm.dir_layer = -1;
-  prm.d_out = d_out; prm.hd = c.HD();
+  prm.d_out = d_out; prm.bits = (uint32_t*)(c.act + c.al.bits); prm.hd_bits_row0 = (int)(D * cap);
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
@@ -762,7 +766,7 @@ int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
   }
   if ((rc = make_tmap_bf16_2d(&maps.save, c.G(0), (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&maps.hd, c.GHD(), P, W / 2, W / 2, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&maps.x0, c.act + c.al.h0, (uint64_t)D * cap, W, W, 128))) return rc;
+  maps.x0 = maps.hd;
   return launch_chain_bwd(maps, prm, c.s);
 }
 
@@ -803,6 +807,17 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
     else rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// diagnostics: byte offsets of the training workspace regions (tests / scripts inspect saved tensors with them)
+extern "C" int nmx_mlp_debug_layout(const nmx_mlp_plan* p, int64_t* out, int n) {
+  NMX_CHECK_ARG(p && out && n >= 12, "plan, out non-null; n >= 12");
+  const ActLayout a = act_layout(p, p->max_points, true);
+  const int64_t base = p->weights_bytes + dirpe_bytes(p);
+  const int64_t v[12] = {base, a.x0, a.h0, a.h_stride, a.feat, a.hd, a.g0, a.g_stride, a.ghd, a.bits, p->max_points,
+                         (int64_t)p->x0_cols};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
   return 0;
 }
 
