@@ -822,7 +822,8 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaSt
     attr = true;
   }
   int tiles = (prm.P + 127) / 128;
-  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int cap_ctas = (prm.max_ctas > 0 && prm.max_ctas < kNumSMs) ? prm.max_ctas : kNumSMs;
+  int grid = tiles < cap_ctas ? tiles : cap_ctas;
   double flops = 0.0;  // padded flops actually issued to the tensor pipe
   for (int l = 0; l < prm.n_layers; ++l) flops += 2.0 * prm.P * prm.L[l].N * 64.0 * prm.L[l].n_slabs;
   prof_begin(MODE == 1 ? 4 : (prm.save ? 3 : 2), flops, stream);

@@ -572,7 +572,9 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   a.db = g.db;
   int m_tiles = (g.M + 127) / 128;
   int total_kb = (int)((g.P + 63) / 64);
-  int splits = kNumSMs / m_tiles;
+  const int cta_cap = (g.max_ctas > 0 && g.max_ctas < kNumSMs) ? g.max_ctas : kNumSMs;
+  int splits = cta_cap / m_tiles;
+  if (splits < 1) splits = 1;
   if (splits > total_kb) splits = total_kb;
   a.kb_per_cta = (total_kb + splits - 1) / splits;
   splits = (total_kb + a.kb_per_cta - 1) / a.kb_per_cta;

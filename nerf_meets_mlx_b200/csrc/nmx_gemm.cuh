@@ -24,6 +24,7 @@ struct WgradDesc {
   int64_t P; int M, N;                                // M % 64 == 0, N % 64 == 0 (<= 256)
   float* dW; int ldw, w_col; int n_valid;             // only columns < n_valid are accumulated
   float* db;                                          // optional: db[m] += sum_p dY[p, m] (bias gradient), or null
+  int max_ctas;                                       // 0 = all SMs; else cap on the CTA count (concurrent kernels)
 };
 
 // live profiling hooks (nmx_profile_enable): kind 0 layer GEMM, 1 wgrad, 2 chain forward (inference), 3 chain forward

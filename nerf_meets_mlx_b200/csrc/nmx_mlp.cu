@@ -721,7 +721,7 @@ bool chain_bwd_eligible(const nmx_mlp_plan* p) {
 // Fused data-gradient chain (nmx_chain.cu MODE 1): d_hd -> d_feature -> dY_{D-1} -> ... -> dY_0, every one kept in
 // its G slot for the wgrad kernels.  Layer order: dir-layer dgrad, feature dgrad (+ alpha rank-1, mask h_{D-1}),
 // trunk layers D-1 .. 1 (mask h_{l-1}).
-int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
+int backward_chain(const Ctx& c, int64_t row0, int64_t P, int64_t cap, const float* d_out, int max_ctas, cudaStream_t st) {
   nmx_mlp_plan* p = c.p;
   const int W = p->W, D = p->D;
   ChainMaps maps;
@@ -758,16 +758,17 @@ int backward_chain(const Ctx& c, int64_t P, int64_t cap, const float* d_out) {
   prm.head7_layer = -1; prm.rgb_layer = -1; prm.head7_n = 1;
   prm.head7_w_off = (int)p->alpha.w_off; prm.rgb_w_off = (int)p->rgb.w_off;
   prm.uses_dir = 0; prm.pos_last_layer = -1; prm.pos_prefetch_layer = -1; prm.dir_layer = -1;
-  prm.d_out = d_out; prm.bits = (uint32_t*)(c.act + c.al.bits); prm.hd_bits_row0 = (int)(D * cap);
+  prm.d_out = d_out + row0 * 4; prm.bits = (uint32_t*)(c.act + c.al.bits) + row0 * 8; prm.hd_bits_row0 = (int)(D * cap);
+  prm.max_ctas = max_ctas;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
     prm.dbg = dbg & ~3;  // bits 2 (trace), 3 (no mask reads), 4 (no dY stores) apply to the backward chain
   }
-  if ((rc = make_tmap_bf16_2d(&maps.save, c.G(0), (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
-  if ((rc = make_tmap_bf16_2d(&maps.hd, c.GHD(), P, W / 2, W / 2, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&maps.save, c.G(0) + row0 * W, (uint64_t)(D + 1) * cap - row0, W, W, 128))) return rc;
+  if ((rc = make_tmap_bf16_2d(&maps.hd, c.GHD() + row0 * (W / 2), P, W / 2, W / 2, 128))) return rc;
   maps.x0 = maps.hd;
-  return launch_chain_bwd(maps, prm, c.s);
+  return launch_chain_bwd(maps, prm, st);
 }
 
 }  // namespace
@@ -855,31 +856,85 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
             (long long)P, (void*)c.HD(), (void*)c.GHD(), (const void*)hl);
   }
   if (chain_bwd_eligible(p)) {
+    // The data-gradient chain is bound by HBM *writes* (every dY is kept for wgrad; pure writes peak at ~3.9 TB/s on
+    // B200) and the wgrad kernels by HBM *reads*.  NMX_BWD_CHUNKS=K > 1 cuts the pass into K point chunks and runs
+    // wgrad(k) on a second stream, on its own share of the SMs, while the chain works on chunk k+1.  Measured on B200
+    // this mixing does NOT pay (K=4: 7.4 ms vs 6.1 ms for the fine pass: per-SM bandwidth, 4x the wgrad flushes), so
+    // the default is the sequential schedule K = 1; the path is kept for experiments.
+    static cudaStream_t s2 = nullptr;
+    static std::vector<cudaEvent_t> evs;
+    static int n_chunks_cfg = -1, chain_sms_cfg = -1;
+    if (s2 == nullptr) {
+      NMX_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      const char* e1 = getenv("NMX_BWD_CHUNKS");
+      const char* e2 = getenv("NMX_BWD_CHAIN_SMS");
+      n_chunks_cfg = e1 ? atoi(e1) : 1;
+      chain_sms_cfg = e2 ? atoi(e2) : 96;
+      if (n_chunks_cfg < 1) n_chunks_cfg = 1;
+      if (chain_sms_cfg < 8 || chain_sms_cfg > kNumSMs - 8) chain_sms_cfg = 96;
+    }
+    const int64_t tiles = (P + 127) / 128;
+    int K = n_chunks_cfg;
+    if (tiles < (int64_t)4 * kNumSMs * K) K = (int)(tiles / (4 * kNumSMs)) > 0 ? (int)(tiles / (4 * kNumSMs)) : 1;
+    while ((int)evs.size() < K + 2) {
+      cudaEvent_t e;
+      NMX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      evs.push_back(e);
+    }
+    const int64_t chunk_rows = (tiles + K - 1) / K * 128;
+    NMX_CUDA(cudaEventRecord(evs[K], s));  // d_params zeroed (and everything before) -> second stream may start
+    NMX_CUDA(cudaStreamWaitEvent(s2, evs[K], 0));
     // head weight gradients (their data gradients are produced inside the fused chain)
     if ((rc = launch_head_bwd(W / 2, 3, c.HD(), W / 2, params + p->rgb.w_off, d_out, out_cols, 0, P,
-                              d_params + p->rgb.w_off, d_params + p->rgb.b_off, nullptr, 0, s))) return rc;
+                              d_params + p->rgb.w_off, d_params + p->rgb.b_off, nullptr, 0, K > 1 ? s2 : s))) return rc;
     if ((rc = launch_head_bwd(W, 1, hl, W, params + p->alpha.w_off, d_out, out_cols, 3, P, d_params + p->alpha.w_off,
-                              d_params + p->alpha.b_off, nullptr, 0, s))) return rc;
-    if ((rc = backward_chain(c, P, p->max_points, d_out))) return rc;
-    // weight gradients from the saved dY slots: dir layer over [feature | dir PE], feature layer, trunk layers
-    float* dWd = d_params + p->dir.w_off;
-    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
-    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
-    if ((rc = wgrad(c.G(p->D), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
-    for (int l = p->D - 1; l >= 0; --l) {
-      const LinearRef& r = p->trunk[l];
-      const bf16* dY = c.G(l);
-      float* dW = d_params + r.w_off;
-      float* db = d_params + r.b_off;
-      const bool skip_in = (r.in == W + p->in_pos);
-      if (l == 0) {
-        if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
-      } else if (skip_in) {
-        if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
-        if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
-      } else {
-        if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
+                              d_params + p->alpha.b_off, nullptr, 0, K > 1 ? s2 : s))) return rc;
+    for (int k = 0; k < K; ++k) {
+      const int64_t r0 = (int64_t)k * chunk_rows;
+      const int64_t rows = P - r0 < chunk_rows ? P - r0 : chunk_rows;
+      if (rows <= 0) break;
+      const bool alone_chain = (K == 1 || k == 0);            // nothing to overlap with yet: use every SM
+      const bool alone_wgrad = (K == 1 || k == K - 1);        // last chunk: the chain is finished
+      if ((rc = backward_chain(c, r0, rows, p->max_points, d_out, alone_chain ? 0 : chain_sms_cfg, s))) return rc;
+      cudaStream_t sw = K > 1 ? s2 : s;
+      if (K > 1) {
+        NMX_CUDA(cudaEventRecord(evs[k], s));
+        NMX_CUDA(cudaStreamWaitEvent(s2, evs[k], 0));
       }
+      const int wg_ctas = alone_wgrad ? 0 : kNumSMs - chain_sms_cfg;
+      auto wg = [&](const bf16* dY, int dy_cols, const bf16* X, int x_cols, int x_col, int M, int N, int n_valid,
+                    float* dW, int ldw, int w_col, float* db) {
+        WgradDesc g{};
+        g.dY = dY + r0 * dy_cols; g.dy_cols = dy_cols; g.dy_ld = dy_cols; g.dy_col = 0;
+        g.X = X + r0 * x_cols; g.x_cols = x_cols; g.x_ld = x_cols; g.x_col = x_col;
+        g.P = rows; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid; g.db = db;
+        g.max_ctas = wg_ctas;
+        return launch_wgrad(g, sw);
+      };
+      // weight gradients from the saved dY slots: dir layer over [feature | dir PE], feature layer, trunk layers
+      float* dWd = d_params + p->dir.w_off;
+      if ((rc = wg(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
+      if ((rc = wg(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
+      if ((rc = wg(c.G(p->D), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
+      for (int l = p->D - 1; l >= 0; --l) {
+        const LinearRef& r = p->trunk[l];
+        const bf16* dY = c.G(l);
+        float* dW = d_params + r.w_off;
+        float* db = d_params + r.b_off;
+        const bool skip_in = (r.in == W + p->in_pos);
+        if (l == 0) {
+          if ((rc = wg(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
+        } else if (skip_in) {
+          if ((rc = wg(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
+          if ((rc = wg(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
+        } else {
+          if ((rc = wg(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
+        }
+      }
+    }
+    if (K > 1) {  // join: the caller's stream continues only after the second stream's last wgrad
+      NMX_CUDA(cudaEventRecord(evs[K + 1], s2));
+      NMX_CUDA(cudaStreamWaitEvent(s, evs[K + 1], 0));
     }
     return 0;
   }
