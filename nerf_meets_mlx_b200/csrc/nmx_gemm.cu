@@ -437,14 +437,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     tc_fence_after();
     const int m = m_tile * 128 + q * 32 + lane;
     float* wrow = args.dW + (size_t)m * args.ldw + args.w_col;
+    // flush: one vector reduction (red.global.add.v4.f32, 16 B) per 4 columns when the row start is 16 B aligned --
+    // 4x fewer L2 atomic operations than scalar adds; the scalar path handles odd leading dimensions (63 / 283 / 319)
+    const bool vec_ok = ((args.ldw & 3) == 0) && ((args.w_col & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(args.dW) & 15) == 0);
     for (int c0 = 0; c0 < N; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(q * 32) << 16), r);
       tmem_ld_wait();
       if (m < args.M) {
+        if (vec_ok && c0 + 32 <= args.n_valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < args.n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c0 + j),
+                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                         "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < args.n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+        }
       }
     }
     if (want_db) {

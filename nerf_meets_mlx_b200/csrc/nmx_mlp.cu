@@ -938,59 +938,82 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
     }
     return 0;
   }
-  if (p->cfg.use_viewdirs) {
-    // rgb head: d_hd_pre = (d_rgb W_rgb) * [hd > 0]; dW_rgb, db_rgb
-    if ((rc = launch_head_bwd(W / 2, 3, c.HD(), W / 2, params + p->rgb.w_off, d_out, out_cols, 0, P,
-                              d_params + p->rgb.w_off, d_params + p->rgb.b_off, c.GHD(), W / 2, s))) return rc;
-    // alpha head: dW_alpha, db_alpha (its d_h is the rank-1 term of the feature dgrad epilogue)
-    if ((rc = launch_head_bwd(W, 1, hl, W, params + p->alpha.w_off, d_out, out_cols, 3, P, d_params + p->alpha.w_off,
-                              d_params + p->alpha.b_off, nullptr, 0, s))) return rc;
-    // dir layer: wgrad over [feature | dir PE], bias, dgrad to feature
-    float* dWd = d_params + p->dir.w_off;
-    if ((rc = wgrad(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
-    if ((rc = wgrad(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
-    GemmDesc g{};
-    g.A0 = c.GHD(); g.a0_rows = P; g.a0_cols = W / 2; g.a0_ld = W / 2; g.a0_k = W / 2;
-    g.B = c.ws + p->wt_dir; g.b_rows = W; g.b_cols = W / 2; g.b_ld = W / 2;
-    g.M = P; g.N = W; g.D = c.G(0); g.ldd = W;
-    if ((rc = launch_gemm(g, s))) return rc;
-    // feature layer: wgrad, bias, dgrad (+ alpha rank-1 term, ReLU mask of h_{D-1})
-    if ((rc = wgrad(c.G(0), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
-    GemmDesc f{};
-    f.A0 = c.G(0); f.a0_rows = P; f.a0_cols = W; f.a0_ld = W; f.a0_k = W;
-    f.B = c.ws + p->wt_feat; f.b_rows = W; f.b_cols = W; f.b_ld = W;
-    f.M = P; f.N = W; f.D = c.G(1); f.ldd = W; f.mask = hl; f.ldmask = W;
-    f.row_vec = d_out + 3; f.row_stride = out_cols; f.col_vec = params + p->alpha.w_off;
-    if ((rc = launch_gemm(f, s))) return rc;
-    cur = 1;
-  } else {
-    // no-view head: d_h = (d_out W_out) * [h > 0]; dW_out, db_out
-    if ((rc = launch_head_bwd(W, p->cfg.out_ch, hl, W, params + p->outl.w_off, d_out, out_cols, 0, P,
-                              d_params + p->outl.w_off, d_params + p->outl.b_off, c.G(0), W, s))) return rc;
-    cur = 0;
-  }
-  for (int l = p->D - 1; l >= 0; --l) {
-    const LinearRef& r = p->trunk[l];
-    const bf16* dY = c.G(cur);
-    float* dW = d_params + r.w_off;
-    bool skip_in = (r.in == W + p->in_pos);
-    float* db = d_params + r.b_off;
-    if (l == 0) {
-      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
-    } else if (skip_in) {
-      if ((rc = wgrad(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
-      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
-    } else {
-      if ((rc = wgrad(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
-    }
-    if (l >= 1) {
+  // Layer-by-layer path (nets the fused chain does not cover).  With NMX_BWD_L2_ROWS=R the pass runs over windows of
+  // R points so that the two ping-pong gradient buffers (always the SAME first R rows) stay L2-resident.
+  auto run_window = [&](int64_t r0, int64_t rows) -> int {
+    const bf16* hl_r = hl + r0 * W;
+    const float* d_out_r = d_out + r0 * out_cols;
+    int cur = 0;
+    auto wgrad = [&](const bf16* dY, int dy_cols, const bf16* X, int x_cols, int x_col, int M, int N, int n_valid,
+                     float* dW, int ldw, int w_col, float* db) {
+      WgradDesc g{};
+      g.dY = dY; g.dy_cols = dy_cols; g.dy_ld = dy_cols; g.dy_col = 0;
+      g.X = X; g.x_cols = x_cols; g.x_ld = x_cols; g.x_col = x_col;
+      g.P = rows; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid; g.db = db;
+      return launch_wgrad(g, s);
+    };
+    if (p->cfg.use_viewdirs) {
+      // rgb head: d_hd_pre = (d_rgb W_rgb) * [hd > 0]; dW_rgb, db_rgb
+      if ((rc = launch_head_bwd(W / 2, 3, (c.HD() + r0 * (W / 2)), W / 2, params + p->rgb.w_off, d_out_r, out_cols, 0, rows,
+                                d_params + p->rgb.w_off, d_params + p->rgb.b_off, c.GHD(), W / 2, s))) return rc;
+      // alpha head: dW_alpha, db_alpha (its d_h is the rank-1 term of the feature dgrad epilogue)
+      if ((rc = launch_head_bwd(W, 1, hl_r, W, params + p->alpha.w_off, d_out_r, out_cols, 3, rows, d_params + p->alpha.w_off,
+                                d_params + p->alpha.b_off, nullptr, 0, s))) return rc;
+      // dir layer: wgrad over [feature | dir PE], bias, dgrad to feature
+      float* dWd = d_params + p->dir.w_off;
+      if ((rc = wgrad(c.GHD(), W / 2, (c.FEAT() + r0 * W), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
+      if ((rc = wgrad(c.GHD(), W / 2, (c.X0() + r0 * p->x0_cols), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
       GemmDesc g{};
-      g.A0 = dY; g.a0_rows = P; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
-      g.B = c.ws + p->wt_off[l]; g.b_rows = W; g.b_cols = W; g.b_ld = W;
-      g.M = P; g.N = W; g.D = c.G(cur ^ 1); g.ldd = W; g.mask = c.H(l - 1); g.ldmask = W;
+      g.A0 = c.GHD(); g.a0_rows = rows; g.a0_cols = W / 2; g.a0_ld = W / 2; g.a0_k = W / 2;
+      g.B = c.ws + p->wt_dir; g.b_rows = W; g.b_cols = W / 2; g.b_ld = W / 2;
+      g.M = rows; g.N = W; g.D = c.G(0); g.ldd = W;
       if ((rc = launch_gemm(g, s))) return rc;
-      cur ^= 1;
+      // feature layer: wgrad, bias, dgrad (+ alpha rank-1 term, ReLU mask of h_{D-1})
+      if ((rc = wgrad(c.G(0), W, hl_r, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
+      GemmDesc f{};
+      f.A0 = c.G(0); f.a0_rows = rows; f.a0_cols = W; f.a0_ld = W; f.a0_k = W;
+      f.B = c.ws + p->wt_feat; f.b_rows = W; f.b_cols = W; f.b_ld = W;
+      f.M = rows; f.N = W; f.D = c.G(1); f.ldd = W; f.mask = hl_r; f.ldmask = W;
+      f.row_vec = d_out_r + 3; f.row_stride = out_cols; f.col_vec = params + p->alpha.w_off;
+      if ((rc = launch_gemm(f, s))) return rc;
+      cur = 1;
+    } else {
+      // no-view head: d_h = (d_out W_out) * [h > 0]; dW_out, db_out
+      if ((rc = launch_head_bwd(W, p->cfg.out_ch, hl_r, W, params + p->outl.w_off, d_out_r, out_cols, 0, rows,
+                                d_params + p->outl.w_off, d_params + p->outl.b_off, c.G(0), W, s))) return rc;
+      cur = 0;
     }
+    for (int l = p->D - 1; l >= 0; --l) {
+      const LinearRef& r = p->trunk[l];
+      const bf16* dY = c.G(cur);
+      float* dW = d_params + r.w_off;
+      bool skip_in = (r.in == W + p->in_pos);
+      float* db = d_params + r.b_off;
+      if (l == 0) {
+        if ((rc = wgrad(dY, W, (c.X0() + r0 * p->x0_cols), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
+      } else if (skip_in) {
+        if ((rc = wgrad(dY, W, (c.X0() + r0 * p->x0_cols), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
+        if ((rc = wgrad(dY, W, (c.H(l - 1) + r0 * W), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
+      } else {
+        if ((rc = wgrad(dY, W, (c.H(l - 1) + r0 * W), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
+      }
+      if (l >= 1) {
+        GemmDesc g{};
+        g.A0 = dY; g.a0_rows = rows; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
+        g.B = c.ws + p->wt_off[l]; g.b_rows = W; g.b_cols = W; g.b_ld = W;
+        g.M = rows; g.N = W; g.D = c.G(cur ^ 1); g.ldd = W; g.mask = (c.H(l - 1) + r0 * W); g.ldmask = W;
+        if ((rc = launch_gemm(g, s))) return rc;
+        cur ^= 1;
+      }
+    }
+    return 0;
+  };
+  static int64_t l2_rows = -1;
+  if (l2_rows < 0) { const char* e = getenv("NMX_BWD_L2_ROWS"); l2_rows = e ? atoll(e) : 0; }
+  if (l2_rows > 0 && l2_rows % 128 == 0) {
+    for (int64_t r0 = 0; r0 < P; r0 += l2_rows)
+      if ((rc = run_window(r0, P - r0 < l2_rows ? P - r0 : l2_rows))) return rc;
+    return 0;
   }
-  return 0;
+  return run_window(0, P);
 }
