@@ -430,6 +430,13 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     const uint32_t ring16 = smem_u32(s_ring) >> 4;
     constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      // The previous tile's last layer signalled act_ready for the store warp only (training) -- no MMA consumed it.
+      // An mbarrier parity wait can only tell the current phase from the one before, so this warp must never get two
+      // phases ahead of a barrier: observe those signals before waiting for this tile's first ones.
+      if (it > 0 && save && !prm.L[NL - 1].feeds_next) {
+        const int nck_last = prm.L[NL - 1].N / 64;
+        for (int c = 0; c < nck_last; ++c) mbar_wait(&act_ready[c], ((acbits >> c) & 1u) ^ 1u);
+      }
       if (MODE == 1) acbits ^= 0x3u;  // step A (d_hd) signals chunks 0,1 before the first layer
       for (int l = 0; l < NL; ++l, ++lcount) {
         const int as = lcount & 1;
@@ -509,7 +516,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           for (int c = 0; c < nck; ++c) {
             mbar_wait(&act_ready[c], (acbits >> c) & 1u);
             if (elect_one() && !(prm.dbg & 16)) {
-              if (kind == 1) tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, row0);
+              if (kind == 1 && (prm.dbg & 32))  // experiment: chunk-major planes, each store one contiguous 16 KB block
+                tma_store_2d(&maps.save, s_act + c * kChunkBytes, 0, prm.L[l].save_row0 * 4 + c * prm.cap + tile * 128);
+              else if (kind == 1) tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, row0);
               else if (kind == 2) tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
               tma_store_commit();
             }

@@ -47,6 +47,7 @@ struct ChainParams {
   int hd_bits_row0;   // backward: slot of the dir-layer activation hd (masks step A)
   // backward chain only: d_raw [P, 4] fp32 (d_rgb, d_sigma)
   const float* d_out;
+  int cap;       // rows per slot of the activation store (experiment NMX_CHAIN_DBG bit 5: chunk-major store layout)
   int max_ctas;  // 0 = one CTA per SM; smaller values leave SMs to a kernel running concurrently on another stream
   int dbg;  // experiments only (NMX_CHAIN_DBG): bit 0 = no weight TMA traffic, bit 1 = epilogue math skipped
 };

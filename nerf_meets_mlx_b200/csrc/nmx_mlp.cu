@@ -696,7 +696,10 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   prm.P = (int)npts; prm.save = c.training ? 1 : 0; prm.params = c.params; prm.out = out; prm.out_cols = out_cols;
   if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
   if (c.training) {
-    if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
+    prm.cap = (int)cap;
+    if (prm.dbg & 32) {
+      if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap * 4, 64, 64, 128))) return rc;
+    } else if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
     if (p->cfg.use_viewdirs) {
       if ((rc = make_tmap_bf16_2d(&maps.hd, c.HD(), npts, W / 2, W / 2, 128))) return rc;
     } else {
