@@ -35,8 +35,8 @@ constexpr int kEpiWarp0 = 0;                // warps 0..15 epilogue (TMEM lane q
 constexpr int kStoreWarp = 16;              // activation-store issuer (training) + TMEM alloc/dealloc
 constexpr int kTmaWarp = 17;
 constexpr int kMmaWarp = 18;
-constexpr int kMaskWarp = 19;             // backward only: TMA loader of the saved-activation (ReLU mask) chunks
-constexpr int kThreads = 20 * 32;
+constexpr int kMaskWarp = 19;             // backward: ReLU sign-bit loader; forward: fused input encoder
+constexpr int kThreads = 20 * 32;         // (inference: the idle store warp is the second input encoder)
 constexpr int kStages = 3;
 constexpr int kSlabBytes = 256 * 64 * 2;   // one piece of weights: up to 256 output rows x 64-wide K slab
 constexpr int kChunkBytes = 128 * 64 * 2;  // one 128-row x 64-col bf16 activation chunk
@@ -273,6 +273,36 @@ __device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, c
   fence_proxy_async_smem();
 }
 
+// Fused input encoding of one point (enc_kind 1, 10 position bands): the same fp32 operations as encode_rays_kernel
+// (pos = o + z d with separate mul / add, band k^2, full-range sincosf), written as the 128 B swizzled row of the
+// position chunk.  Channel order (models/embedding.py:35-71): [x y z | per band k: sin(k^2 xyz), cos(k^2 xyz)] + 0 pad.
+__device__ __forceinline__ void encode_pos_row(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
+                                               long long p, int n, bool valid, uint32_t row_addr, uint32_t swz) {
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = 0.0f;
+  if (valid) {
+    const long long b = p / n;
+    const float* r = rays + b * ray_stride;
+    const float zz = __ldg(z + p);
+    const float px = __fadd_rn(__ldg(r + 0), __fmul_rn(zz, __ldg(r + 3)));
+    const float py = __fadd_rn(__ldg(r + 1), __fmul_rn(zz, __ldg(r + 4)));
+    const float pz = __fadd_rn(__ldg(r + 2), __fmul_rn(zz, __ldg(r + 5)));
+    v[0] = px; v[1] = py; v[2] = pz;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float f = (float)(k * k);
+      sincosf(__fmul_rn(px, f), &v[3 + 6 * k + 0], &v[3 + 6 * k + 3]);
+      sincosf(__fmul_rn(py, f), &v[3 + 6 * k + 1], &v[3 + 6 * k + 4]);
+      sincosf(__fmul_rn(pz, f), &v[3 + 6 * k + 2], &v[3 + 6 * k + 5]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sts128(row_addr + ((((uint32_t)j) ^ swz) << 4), pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+}
+
 // MODE 0: forward (bias + ReLU epilogue, heads).  MODE 1: backward data-gradient chain (models/NeRF.py backward of
 // 201-243): step A computes d_hd = (d_rgb W_rgb) * [hd > 0] on the CUDA cores, then every layer is
 // dX = dY W (W^T copies as the K-major B operand), with the ReLU mask of the saved activation (and the alpha head's
@@ -364,7 +394,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if (it == 0 && MODE == 0) {
+      if (it == 0 && MODE == 0 && !prm.enc_fused) {
         if (elect_one()) {
           mbar_arrive_expect_tx(x0pos_full, kChunkBytes);
           tma_load_2d(s_x0, &maps.x0, x0pos_full, 0, tile * 128);
@@ -394,7 +424,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (MODE == 0 && l == 1 && it > 0 && prm.uses_dir) {
+        if (MODE == 0 && !prm.enc_fused && l == 1 && it > 0 && prm.uses_dir) {
           // this tile's view-dir chunk: the previous tile's dir-layer MMAs must have finished reading the buffer
           mbar_wait(x0dir_empty, (uint32_t)((it - 1) & 1));
           if (elect_one()) {
@@ -403,7 +433,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           }
           __syncwarp();
         }
-        if (MODE == 0 && l == prm.pos_prefetch_layer) {
+        if (MODE == 0 && !prm.enc_fused && l == prm.pos_prefetch_layer) {
           const int ntile = tile + gridDim.x;
           if (ntile < num_tiles) {  // next tile's position chunk, once this tile's last reader (skip layer) is done
             mbar_wait(x0pos_empty, (uint32_t)(it & 1));
@@ -488,7 +518,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
         if (prm.L[l].feeds_next || save) acbits ^= (prm.L[l].N > 128 ? 0xFu : 0x3u);
       }
     }
-  } else if (warp == kStoreWarp) {
+  } else if (warp == kStoreWarp && (MODE == 1 || save || !prm.enc_fused)) {
     // ====================================================== activation-store issuer (training)
     if (save) {
       uint32_t acbits = 0;
@@ -542,11 +572,83 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
     }
-  } else if (warp == kMaskWarp) {
+  } else if (warp == kMaskWarp || (MODE == 0 && warp == kStoreWarp && !save && prm.enc_fused)) {
     // ====================================================== ReLU sign-bit loader, backward only
     // Masked step s (step A, then every masked layer) reads slot s & 1: a contiguous 4 KB tile of sign bits, bulk-copied
     // one step ahead; a slot is refilled once all sixteen epilogue warps have arrived on bits_empty.
-    if (MODE == 1 && !(prm.dbg & 8)) {
+    if (MODE == 0 && prm.enc_fused) {
+      // ---- fused input encoder (forward), one tile ahead of the MMA warp.  Training: this warp alone (four rows per
+      // lane; the tile period is long enough).  Inference: the idle store warp takes rows 64..127.
+      const int n_enc = save ? 1 : 2;
+      const int ew = warp == kMaskWarp ? 0 : 1;
+      const int rows_per_lane = 4 / n_enc;
+      const bool leader = ew == 0 && lane == 0;  // arrives on the barriers and issues the x0 stores (training)
+      auto enc_sync = [&]() {
+        if (n_enc == 2) asm volatile("bar.sync 2, 64;" ::: "memory");
+        else __syncwarp();
+      };
+      const uint32_t x0_addr = smem_u32(s_x0);
+      const uint4* dpe = reinterpret_cast<const uint4*>(prm.dir_pe);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        // position chunk: its last reader of the previous tile is the skip layer
+        if (it > 0) mbar_wait(x0pos_empty, (uint32_t)((it - 1) & 1));
+        if (save && it > 0) {  // the x0 stores of the previous tile read these chunks
+          if (leader) tma_store_wait_read<0>();
+          enc_sync();
+        }
+#pragma unroll 1
+        for (int rr = 0; rr < rows_per_lane; ++rr) {
+          const int row_local = ew * 64 + rr * 32 + lane;
+          const int row = tile * 128 + row_local;
+          encode_pos_row(prm.rays, prm.ray_stride, prm.z, prm.p0 + row, prm.n_per_ray, row < prm.P,
+                         x0_addr + (uint32_t)row_local * 128u, (uint32_t)(row_local & 7));
+        }
+        fence_proxy_async_smem();
+        enc_sync();
+        if (leader) {
+          mbar_arrive(x0pos_full);
+          if (save) {  // wgrad of the first / skip layer reads the encoded tile from HBM
+            tma_store_2d(&maps.x0, s_x0, 0, tile * 128);
+            tma_store_commit();
+          }
+        }
+        if (prm.uses_dir) {
+          // view-dir chunk: gathered from the per-ray table; its last reader of the previous tile is the dir layer
+          if (it > 0) mbar_wait(x0dir_empty, (uint32_t)((it - 1) & 1));
+#pragma unroll 1
+          for (int rr = 0; rr < rows_per_lane; ++rr) {
+            const int row_local = ew * 64 + rr * 32 + lane;
+            const int row = tile * 128 + row_local;
+            const uint32_t ra = x0_addr + kChunkBytes + (uint32_t)row_local * 128u;
+            const uint32_t swz = (uint32_t)(row_local & 7);
+            uint4 d[8];
+            if (row < prm.P) {
+              const long long b = (prm.p0 + row) / prm.n_per_ray - prm.b0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = __ldg(dpe + b * 8 + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(ra + ((((uint32_t)j) ^ swz) << 4), d[j].x, d[j].y, d[j].z, d[j].w);
+          }
+          fence_proxy_async_smem();
+          enc_sync();
+          if (leader) {
+            mbar_arrive(x0dir_full);
+            if (save) {
+              tma_store_2d(&maps.x0, s_x0 + kChunkBytes, prm.x0_dir_col, tile * 128);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      if (save && leader) tma_store_wait<0>();
+      __syncwarp();
+    }
+    if (MODE == 1 && warp == kMaskWarp && !(prm.dbg & 8)) {
       uint32_t step = 0;
       auto fill = [&](int row0) {
         const uint32_t slot = step & 1u;

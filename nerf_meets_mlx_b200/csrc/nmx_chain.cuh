@@ -47,6 +47,16 @@ struct ChainParams {
   int hd_bits_row0;   // backward: slot of the dir-layer activation hd (masks step A)
   // backward chain only: d_raw [P, 4] fp32 (d_rgb, d_sigma)
   const float* d_out;
+  // forward, fused input encoding (enc_fused != 0): a dedicated warp evaluates pos = o + z d and the Embedder PE
+  // (10 position bands, models/embedding.py:35-71) for the next tile straight into the shared-memory input chunks;
+  // the per-ray view-dir PE (dir_pe [rays, 64] bf16) is gathered.  p0 / b0: first point / ray of this launch.
+  int enc_fused;
+  const float* rays;
+  int ray_stride;
+  const float* z;
+  const void* dir_pe;
+  long long p0, b0;
+  int n_per_ray;
   int cap;       // rows per slot of the activation store (experiment NMX_CHAIN_DBG bit 5: chunk-major store layout)
   int max_ctas;  // 0 = one CTA per SM; smaller values leave SMs to a kernel running concurrently on another stream
   int dbg;  // experiments only (NMX_CHAIN_DBG): bit 0 = no weight TMA traffic, bit 1 = epilogue math skipped

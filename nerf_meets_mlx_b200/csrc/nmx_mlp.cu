@@ -304,7 +304,7 @@ head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ W
   }
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;
   const int64_t gstride = (int64_t)gridDim.x * nwarps;
-#pragma unroll 2
+#pragma unroll 4
   for (int64_t p = gw; p < P; p += gstride) {
     bf16 hv[CPL];
     if constexpr (CPL == 8) *reinterpret_cast<uint4*>(hv) = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + lane * CPL));
@@ -350,7 +350,7 @@ head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ W
 template <int CPL>
 int launch_head_bwd_nout(int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
                          int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
-  const int blocks = kNumSMs * 2;
+  const int blocks = kNumSMs * 6;  // streaming kernel: enough warps in flight to cover HBM latency
 #define NMX_HB(NO)                                                                                               \
   case NO:                                                                                                       \
     head_bwd_kernel<CPL, NO><<<blocks, 256, 0, s>>>(h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd);          \
@@ -536,10 +536,31 @@ struct Ctx {
   bf16* GHD() const { return (bf16*)(act + al.ghd); }
 };
 
+// the chain kernel can evaluate the Embedder PE itself (enc_kind 1 with the reference's 10 position bands)
+bool enc_fused_ok(const nmx_mlp_plan* p, int enc_kind) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("NMX_DISABLE_FUSED_ENC");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && enc_kind == 1 && chain_eligible(p) && p->cfg.n_freqs_pos == 10 && p->in_pos == 63 &&
+         (p->dir_pad == 0 || p->dir_pad == 64);
+}
+
 int encode_chunk(const Ctx& c, const float* x_or_rays, int ray_stride, const float* z, const float* bands, int64_t p0,
                  int64_t npts, int n) {
   nmx_mlp_plan* p = c.p;
   int kind = c.enc_kind;
+  if (kind == 1 && enc_fused_ok(p, kind)) {  // only the per-ray view-dir table; positions are encoded inside the chain
+    const int64_t b0 = p0 / n, b1 = (p0 + npts - 1) / n;
+    bf16* dir_pe = (bf16*)(c.ws + p->weights_bytes);
+    if (p->dir_pad > 0) {
+      encode_dirs_kernel<<<grid_for((b1 - b0 + 1) * p->dir_pad, 256, 8), 256, 0, c.s>>>(
+          x_or_rays, ray_stride, dir_pe, b0, b1 - b0 + 1, p->cfg.n_freqs_dir, p->dir_pad);
+      NMX_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   if (kind == 1) {
     const int64_t b0 = p0 / n, b1 = (p0 + npts - 1) / n;
     bf16* dir_pe = (bf16*)(c.ws + p->weights_bytes);
@@ -631,7 +652,9 @@ bool chain_eligible(const nmx_mlp_plan* p) {
          p->D >= 2;
 }
 
-int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_cols) {
+struct EncIn { const float* rays; int ray_stride; const float* z; int64_t p0; int n; };
+
+int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_cols, const EncIn* enc) {
   nmx_mlp_plan* p = c.p;
   const int W = p->W, D = p->D;
   ChainMaps maps;
@@ -693,6 +716,10 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
     prm.dbg = dbg;
   }
   prm.bits = (c.training && chain_bwd_eligible(p)) ? (uint32_t*)(c.act + c.al.bits) : nullptr;
+  if (enc != nullptr && enc_fused_ok(p, c.enc_kind)) {
+    prm.enc_fused = 1; prm.rays = enc->rays; prm.ray_stride = enc->ray_stride; prm.z = enc->z;
+    prm.dir_pe = c.ws + p->weights_bytes; prm.p0 = enc->p0; prm.b0 = enc->p0 / enc->n; prm.n_per_ray = enc->n;
+  }
   prm.P = (int)npts; prm.save = c.training ? 1 : 0; prm.params = c.params; prm.out = out; prm.out_cols = out_cols;
   if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
   if (c.training) {
@@ -799,7 +826,10 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   if (c.training) {
     c.al = act_layout(p, p->max_points, true);
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
-    if (chain_eligible(p)) return forward_chain(c, P, p->max_points, out, out_cols);
+    if (chain_eligible(p)) {
+      EncIn ei{x_or_rays, ray_stride, z, 0, n};
+      return forward_chain(c, P, p->max_points, out, out_cols, &ei);
+    }
     return forward_chunk(c, P, out, out_cols);
   }
   int64_t cap = infer_cap(p);
@@ -807,7 +837,8 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t npts = P - p0 < cap ? P - p0 : cap;
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
-    if (chain_eligible(p)) rc = forward_chain(c, npts, cap, out + p0 * out_cols, out_cols);
+    EncIn ei{x_or_rays, ray_stride, z, p0, n};
+    if (chain_eligible(p)) rc = forward_chain(c, npts, cap, out + p0 * out_cols, out_cols, &ei);
     else rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols);
     if (rc) return rc;
   }
