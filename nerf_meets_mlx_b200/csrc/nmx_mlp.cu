@@ -56,7 +56,7 @@ bool chain_eligible(const nmx_mlp_plan* p);
 int64_t infer_cap(const nmx_mlp_plan* p) { return chain_eligible(p) ? (int64_t)kNumSMs * 128 * 16 : kInferChunk; }
 
 struct ActLayout {
-  int64_t x0, h0, feat, hd, g0, ghd, bits, dsig, total;
+  int64_t x0, h0, feat, hd, g0, ghd, bits, gfold, dsig, total;
   int64_t h_stride;  // bytes between consecutive saved trunk activations (0 = ping-pong of 2 buffers)
   int64_t g_stride;  // bytes between gradient buffers: 2 ping-pong buffers, or D+1 saved dY slots (fused chain)
 };
@@ -74,7 +74,7 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   off += hbytes * (training ? p->D : 2);
   a.feat = off; off += hbytes;
   a.hd = off; off += x0_only ? 0 : align256(cap * (p->W / 2) * 2);
-  a.g0 = a.ghd = a.bits = a.dsig = 0;
+  a.g0 = a.ghd = a.bits = a.gfold = a.dsig = 0;
   a.g_stride = hbytes;
   if (training) {
     // fused backward chain: every layer's dY is kept for the wgrad kernels (slots 0..D-1 = dY_l, slot D = d_feature)
@@ -82,6 +82,8 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
     a.ghd = off; off += align256(cap * (p->W / 2) * 2);
     // ReLU sign bits (32 B per point and slot): slots 0..D-1 = h_l, slot D = hd
     a.bits = off; if (chain_bwd_eligible(p)) off += align256(cap * 32) * (p->D + 1);
+    // fp32 scratch G = d_hd^T h_{D-1} [W/2, W] of the feature / dir-layer weight-gradient folding
+    a.gfold = off; if (chain_bwd_eligible(p)) off += align256((int64_t)(p->W / 2) * p->W * 4);
   }
   a.total = off;
   return a;
@@ -345,6 +347,45 @@ head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ W
   __syncthreads();
   for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) atomicAdd(dW + i, s_acc[i]);
   if (threadIdx.x < NOUT) atomicAdd(db + threadIdx.x, s_acc[NOUT * K + threadIdx.x]);
+}
+
+// Weight gradients of the feature layer and of the dir layer's feature part from G = d_hd^T h_{D-1} (no activation sits
+// between feature_linear and list_linears_dir[0], models/NeRF.py:231-236, so the two Linears compose):
+//   dW_dir[o, j]  = sum_k G[o,k] Wf[j,k] + db_dir[o] bf[j]      (= d_hd^T feature,   feature = h Wf^T + bf)
+//   dW_feat[j, k] = sum_o Wd[o,j] G[o,k]                        (= d_feature^T h,    d_feature = d_hd Wd[:, :W])
+//   db_feat[j]    = sum_o db_dir[o] Wd[o,j]
+// with the bf16-rounded weights the tensor-core layers used.  Neither `feature` nor `d_feature` has to be kept in HBM.
+__global__ void __launch_bounds__(256)
+fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__ db_dir, const float* __restrict__ Wf,
+                          const float* __restrict__ bf, const float* __restrict__ Wd, int ldwd, int W, int Wh,
+                          float* __restrict__ dWd, float* __restrict__ dWf, float* __restrict__ dbf) {
+  extern __shared__ float sh[];  // W floats
+  const int t = threadIdx.x;
+  if ((int)blockIdx.x < Wh) {  // one dir-layer output row o: dW_dir[o, 0:W]
+    const int o = blockIdx.x;
+    for (int k = t; k < W; k += blockDim.x) sh[k] = G[(size_t)o * W + k];
+    __syncthreads();
+    for (int j = t; j < W; j += blockDim.x) {
+      float acc = 0.0f;
+      const float* w = Wf + (size_t)j * W;
+      for (int k = 0; k < W; ++k) acc += sh[k] * __bfloat162float(__float2bfloat16_rn(w[k]));
+      dWd[(size_t)o * ldwd + j] += acc + db_dir[o] * bf[j];
+    }
+  } else {  // one feature-layer output row j: dW_feat[j, 0:W], db_feat[j]
+    const int j = blockIdx.x - Wh;
+    for (int o = t; o < Wh; o += blockDim.x) sh[o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldwd + j]));
+    __syncthreads();
+    for (int k = t; k < W; k += blockDim.x) {
+      float acc = 0.0f;
+      for (int o = 0; o < Wh; ++o) acc += sh[o] * G[(size_t)o * W + k];
+      dWf[(size_t)j * W + k] += acc;
+    }
+    if (t == 0) {
+      float acc = 0.0f;
+      for (int o = 0; o < Wh; ++o) acc += db_dir[o] * sh[o];
+      dbf[j] += acc;
+    }
+  }
 }
 
 template <int CPL>
@@ -687,7 +728,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
     for (int k = 0; k < 4; ++k) f.src[k] = k;
     f.bits_row0 = -1;
     f.n_slabs = 4; f.N = W; f.relu = 0; f.bias_off = (int)p->feat.b_off; f.feeds_next = 1;
-    f.save_kind = c.training ? 1 : 0; f.save_row0 = (int)(D * cap);
+    f.save_kind = (c.training && !chain_bwd_eligible(p)) ? 1 : 0; f.save_row0 = (int)(D * cap);
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wf_feat, W, W, W, 128))) return rc;
     ++nl;
     ChainLayerDesc& d = prm.L[nl];
@@ -762,7 +803,7 @@ int backward_chain(const Ctx& c, int64_t row0, int64_t P, int64_t cap, const flo
   {  // d_feature = d_hd . W_dir[:, 0:W]   (K = W/2 over the dir layer's outputs)
     ChainLayerDesc& d = prm.L[nl];
     d.src[0] = 0; d.src[1] = 1; d.n_slabs = 2; d.N = W; d.feeds_next = 1; d.epi = 0;
-    d.save_kind = 1; d.save_row0 = (int)(D * cap);
+    d.save_kind = 0; d.save_row0 = 0;  // d_feature is consumed on chip only (its weight gradients fold, see below)
     if ((rc = make_tmap_bf16_2d(&maps.w[nl], c.ws + p->wt_dir, W, W / 2, W / 2, 128))) return rc;
     ++nl;
   }
@@ -947,9 +988,10 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
       };
       // weight gradients from the saved dY slots: dir layer over [feature | dir PE], feature layer, trunk layers
       float* dWd = d_params + p->dir.w_off;
-      if ((rc = wg(c.GHD(), W / 2, c.FEAT(), W, 0, W / 2, W, W, dWd, p->dir.in, 0, d_params + p->dir.b_off))) return rc;
+      float* gfold = (float*)(c.act + c.al.gfold);  // G = d_hd^T h_{D-1} (+ db_dir = column sums of d_hd)
+      if (k == 0) NMX_CUDA(cudaMemsetAsync(gfold, 0, (size_t)(W / 2) * W * sizeof(float), sw));
+      if ((rc = wg(c.GHD(), W / 2, hl, W, 0, W / 2, W, W, gfold, W, 0, d_params + p->dir.b_off))) return rc;
       if ((rc = wg(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
-      if ((rc = wg(c.G(p->D), W, hl, W, 0, W, W, W, d_params + p->feat.w_off, W, 0, d_params + p->feat.b_off))) return rc;
       for (int l = p->D - 1; l >= 0; --l) {
         const LinearRef& r = p->trunk[l];
         const bf16* dY = c.G(l);
@@ -965,6 +1007,14 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
           if ((rc = wg(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
         }
       }
+    }
+    {  // feature / dir-layer weight gradients from G (after every chunk's wgrad has been accumulated)
+      cudaStream_t sw = K > 1 ? s2 : s;
+      fold_feature_grads_kernel<<<W / 2 + W, 256, W * sizeof(float), sw>>>(
+          (const float*)(c.act + c.al.gfold), d_params + p->dir.b_off, params + p->feat.w_off, params + p->feat.b_off,
+          params + p->dir.w_off, p->dir.in, W, W / 2, d_params + p->dir.w_off, d_params + p->feat.w_off,
+          d_params + p->feat.b_off);
+      NMX_LAUNCH_CHECK();
     }
     if (K > 1) {  // join: the caller's stream continues only after the second stream's last wgrad
       NMX_CUDA(cudaEventRecord(evs[K + 1], s2));
