@@ -237,7 +237,6 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
       }
       __syncwarp();
       if (signal && lane == 0) mbar_arrive(&act_ready[c]);
-      if (h == 0) trace(tr_on, 1, it, l, 2);
     }
   }
 }
@@ -273,9 +272,35 @@ __device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, c
   fence_proxy_async_smem();
 }
 
-// Fused input encoding of one point (enc_kind 1, 10 position bands): the same fp32 operations as encode_rays_kernel
-// (pos = o + z d with separate mul / add, band k^2, full-range sincosf), written as the 128 B swizzled row of the
-// position chunk.  Channel order (models/embedding.py:35-71): [x y z | per band k: sin(k^2 xyz), cos(k^2 xyz)] + 0 pad.
+// Branch-free sin/cos for the fused encoder: three-term Cody-Waite reduction by pi/2 and the usual degree-7/8 minimax
+// polynomials on [-pi/4, pi/4] (about 1 ulp for |x| < ~1e4; the encoder's arguments are at most 81 * |pos|).  Unlike
+// sincosf it has no slow path, so the compiler can interleave the 30 evaluations of a row; the result is rounded to
+// bf16 right away, which hides the (<= 1 ulp fp32) difference from sincosf.
+__device__ __forceinline__ void sincos_bf(float x, float* sp, float* cp) {
+  const float k = rintf(x * 0.636619747f);
+  float r = fmaf(-k, 1.57079601e+00f, x);
+  r = fmaf(-k, 3.13916473e-07f, r);
+  r = fmaf(-k, 5.39030253e-15f, r);
+  const float z = r * r;
+  float ps = 2.86567956e-6f;
+  ps = fmaf(ps, z, -1.98559923e-4f);
+  ps = fmaf(ps, z, 8.33338592e-3f);
+  ps = fmaf(ps, z, -1.66666672e-1f);
+  float s = fmaf(ps * z, r, r);
+  float pc = 2.44677067e-5f;
+  pc = fmaf(pc, z, -1.38877297e-3f);
+  pc = fmaf(pc, z, 4.16666567e-2f);
+  pc = fmaf(pc, z, -5.00000000e-1f);
+  float c = fmaf(pc, z, 1.0f);
+  const int q = (int)k;
+  const float s2 = (q & 1) ? c : s;
+  const float c2 = (q & 1) ? s : c;
+  *sp = (q & 2) ? -s2 : s2;
+  *cp = ((q + 1) & 2) ? -c2 : c2;
+}
+
+// Fused input encoding of one point (enc_kind 1, 10 position bands): pos = o + z d with separate mul / add and band
+// k^2 exactly as encode_rays_kernel, sin/cos by sincos_bf, written as the 128 B swizzled row of the position chunk.  Channel order (models/embedding.py:35-71): [x y z | per band k: sin(k^2 xyz), cos(k^2 xyz)] + 0 pad.
 __device__ __forceinline__ void encode_pos_row(const float* __restrict__ rays, int ray_stride, const float* __restrict__ z,
                                                long long p, int n, bool valid, uint32_t row_addr, uint32_t swz) {
   float v[64];
@@ -292,9 +317,9 @@ __device__ __forceinline__ void encode_pos_row(const float* __restrict__ rays, i
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
       const float f = (float)(k * k);
-      sincosf(__fmul_rn(px, f), &v[3 + 6 * k + 0], &v[3 + 6 * k + 3]);
-      sincosf(__fmul_rn(py, f), &v[3 + 6 * k + 1], &v[3 + 6 * k + 4]);
-      sincosf(__fmul_rn(pz, f), &v[3 + 6 * k + 2], &v[3 + 6 * k + 5]);
+      sincos_bf(__fmul_rn(px, f), &v[3 + 6 * k + 0], &v[3 + 6 * k + 3]);
+      sincos_bf(__fmul_rn(py, f), &v[3 + 6 * k + 1], &v[3 + 6 * k + 4]);
+      sincos_bf(__fmul_rn(pz, f), &v[3 + 6 * k + 2], &v[3 + 6 * k + 5]);
     }
   }
 #pragma unroll
@@ -702,6 +727,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           const bool signal = prm.L[l].feeds_next || save;
           // the TMA stores of the previous layer's chunks must have finished reading shared memory
           if (save && lcount > 0) mbar_wait(store_done, (lcount - 1) & 1);
+          trace(tr_on, 1, it, l, 3);
           const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
           const uint32_t bias_addr = bias_base + (uint32_t)l * 1024u;
           // sign-bit staging row of this thread (training forward of a net whose backward is the fused chain)
@@ -723,10 +749,10 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           else
             epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
                                 0, hp, rgbp, skip_math, tr_on, it, l, bra);
+          trace(tr_on, 1, it, l, 2);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[as]);
-          trace(tr_on, 1, it, l, 3);
         }
         // ---- register heads: combine the column parts' partial sums (4 values per pass) and write the raw outputs
         const int nvals = vd ? 4 : prm.head7_n;

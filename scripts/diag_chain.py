@@ -41,7 +41,7 @@ if os.environ.get("NMX_CHAIN_DBG", "0") != "0":
         t0 = tr[0, 0, 0, 0, 0]
         g0 = tr[0, 0, 0, 0, 1]
         print(f"--- chain trace save={save} (clocks rel. to start; M* = MMA thread, E* = epilogue warp 2)")
-        print("tile layer |  M:tempty_ok  M:full_ok  M:act_ok(issue)  M:committed |  E:wake  E:ld_done  E:h0_arrived  E:layer_done | period")
+        print("tile layer |  M:tempty_ok  M:full_ok  M:act_ok(issue)  M:committed |  E:wake  E:ld_done  E:layer_done  E:store_done_ok(start) | period")
         prev = None
         for it in range(1, 4):
             for l in range(NLAY):
