@@ -178,7 +178,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     B = RAYS_PER_GPU
-    tr = NeRFTrainer(default_args(N_importance=N_IMPORTANCE, n_depth_samples=N_SAMPLES), device=dev, max_rays=B)
+    # single GPU: the iteration is captured once into a CUDA graph and replayed (no launch gaps); multi-GPU runs eagerly
+    tr = NeRFTrainer(default_args(N_importance=N_IMPORTANCE, n_depth_samples=N_SAMPLES), device=dev, max_rays=B,
+                     use_cuda_graph=(world == 1 and not args.no_graph))
     n_batches = 4
     host = []
     for k in range(n_batches):
@@ -202,6 +204,7 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = L.launch_count()
+        it0 = tr.iteration
         e0.record()
         for i in range(steps):
             fn(warmup + i)
@@ -209,6 +212,8 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = L.launch_count() - launches0
+        if tr._graph is not None:  # replayed iterations launch their kernels from the graph, not through the C ABI
+            launches += (tr.iteration - it0) * tr.graph_launches
         if world > 1:
             tms = torch.tensor([ms], device=dev)
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -228,8 +233,10 @@ def run_ours(args):
     import ctypes
     lib.nmx_profile_enable(1)
     prof_steps = max(1, min(args.steps, 3))
+    graph_mode, tr.use_cuda_graph = tr.use_cuda_graph, False  # the library's event timers need eager launches
     for i in range(prof_steps):
         step_resident(i)
+    tr.use_cuda_graph = graph_mode
     prof = {}
     for kind in range(5):
         ms_k, fl_k, n_k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
@@ -290,6 +297,7 @@ def run_ours(args):
             "config": {"workload": "C3 coarse+fine NeRF training step (reference iteration semantics), 64 stratified + "
                                    "128 importance samples/ray, 8x256 MLPs with view-dir head",
                        "rays_per_gpu": B, "global_rays": rays_total, "parallelism": f"dp{world} ray-sharded",
+                       "cuda_graph": bool(tr._graph is not None),
                        "l2": "per-step working set (~20 GB of saved activations and data gradients) >> 126 MB L2; "
                              "4 rotating input batches"},
             "clocks": clocks,
@@ -355,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the training iteration eagerly (no CUDA graph)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -99,6 +99,11 @@ int nmx_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* 
 int nmx_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2,
                   float eps, int bias_correction, int64_t t, void* stream);
 
+/* same update without bias correction, learning rate read from device memory (lets a captured CUDA graph of the
+ * training iteration follow the reference's decaying schedule, __test_nerf.py:302-305) */
+int nmx_adam_step_lrdev(float* p, const float* g, float* m, float* v, int64_t count, const float* lr_dev, float b1,
+                        float b2, float eps, void* stream);
+
 /* ---------------------------------------------------------------- NeRF MLP (K3), tcgen05/TMEM/TMA */
 /* Opaque plan for one NeRF network (models/NeRF.py:160-243) in its reference geometry.
  * Packed parameter layout (fp32, `params`, count = nmx_mlp_param_count): for each Linear in the order

@@ -391,7 +391,7 @@ fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__
 template <int CPL>
 int launch_head_bwd_nout(int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
                          int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
-  const int blocks = kNumSMs * 6;  // streaming kernel: enough warps in flight to cover HBM latency
+  const int blocks = kNumSMs * 4;  // streaming kernel: exactly the resident blocks (64 regs x 256 threads -> 4 per SM)
 #define NMX_HB(NO)                                                                                               \
   case NO:                                                                                                       \
     head_bwd_kernel<CPL, NO><<<blocks, 256, 0, s>>>(h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd);          \
@@ -957,8 +957,10 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
       evs.push_back(e);
     }
     const int64_t chunk_rows = (tiles + K - 1) / K * 128;
-    NMX_CUDA(cudaEventRecord(evs[K], s));  // d_params zeroed (and everything before) -> second stream may start
-    NMX_CUDA(cudaStreamWaitEvent(s2, evs[K], 0));
+    if (K > 1) {
+      NMX_CUDA(cudaEventRecord(evs[K], s));  // d_params zeroed (and everything before) -> second stream may start
+      NMX_CUDA(cudaStreamWaitEvent(s2, evs[K], 0));
+    }
     // head weight gradients (their data gradients are produced inside the fused chain)
     if ((rc = launch_head_bwd(W / 2, 3, c.HD(), W / 2, params + p->rgb.w_off, d_out, out_cols, 0, P,
                               d_params + p->rgb.w_off, d_params + p->rgb.b_off, nullptr, 0, K > 1 ? s2 : s))) return rc;

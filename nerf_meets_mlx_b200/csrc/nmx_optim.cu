@@ -31,7 +31,8 @@ mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, flo
 // MLX-0.7 Adam (no bias correction) or the standard bias-corrected form.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            int64_t count, float lr, float b1, float b2, float eps, float c1, float c2) {
+            int64_t count, float lr, const float* __restrict__ lr_dev, float b1, float b2, float eps, float c1, float c2) {
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);  // learning rate from device memory (CUDA-graph replays)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
@@ -63,7 +64,16 @@ extern "C" int nmx_adam_step(float* p, const float* g, float* m, float* v, int64
     c1 = 1.0f / (1.0f - powf(b1, (float)t));
     c2 = 1.0f / (1.0f - powf(b2, (float)t));
   }
-  adam_kernel<<<grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, b1, b2, eps, c1, c2);
+  adam_kernel<<<grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, nullptr, b1, b2, eps, c1, c2);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int nmx_adam_step_lrdev(float* p, const float* g, float* m, float* v, int64_t count, const float* lr_dev,
+                                   float b1, float b2, float eps, void* stream) {
+  NMX_CHECK_ARG(count >= 0 && p && g && m && v && lr_dev, "count >= 0; p, g, m, v, lr_dev non-null");
+  if (count == 0) return 0;
+  adam_kernel<<<grid_for(count, 256, 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, 0.0f, lr_dev, b1, b2, eps, 1.0f, 1.0f);
   NMX_LAUNCH_CHECK();
   return 0;
 }

@@ -263,7 +263,9 @@ class AdamMLX:
         self.state = {}
         self.step_count = 0
 
-    def update(self, model, grads=None):
+    def update(self, model, grads=None, lr_dev=None):
+        """`lr_dev`: optional device scalar holding the learning rate (used when the iteration is replayed from a CUDA
+        graph, where a by-value learning rate would be frozen at capture time)."""
         from .. import ops
         g = grads if grads is not None else model.flat.grad
         key = ("shared", g.numel()) if self.shared_state else id(model)
@@ -272,7 +274,7 @@ class AdamMLX:
         m, v = self.state[key]
         self.step_count += 1
         ops.adam_step(model.flat.data, g, m, v, self.learning_rate, self.betas[0], self.betas[1], self.eps,
-                      self.bias_correction, self.step_count)
+                      self.bias_correction, self.step_count, lr_dev=lr_dev)
         model.mark_params_updated()
 
 

@@ -3,7 +3,7 @@ current CUDA stream.  No CPU path exists; every function raises if the extension
 contiguous CUDA tensors."""
 import torch
 
-from ._lib_loader import call, f32, i32, i64, ptr, require_cuda, stream
+from ._lib_loader import NmxError, call, f32, i32, i64, ptr, require_cuda, stream
 
 
 def _f32c(t):
@@ -165,8 +165,15 @@ def mse_fwd_bwd(pred, target, want_grad=True, grad_scale=1.0):
     return loss, d
 
 
-def adam_step(p, g, m, v, lr, b1=0.9, b2=0.999, eps=1e-8, bias_correction=False, t=1):
+def adam_step(p, g, m, v, lr, b1=0.9, b2=0.999, eps=1e-8, bias_correction=False, t=1, lr_dev=None):
     require_cuda(p, g, m, v)
+    if lr_dev is not None:  # learning rate from a device scalar (CUDA-graph replays); MLX-style update only
+        if bias_correction:
+            raise NmxError("adam_step: lr_dev is only supported without bias correction")
+        require_cuda(lr_dev)
+        call("nmx_adam_step_lrdev", ptr(p), ptr(g), ptr(m), ptr(v), i64(p.numel()), ptr(lr_dev), f32(b1), f32(b2), f32(eps),
+             stream())
+        return
     call("nmx_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), i64(p.numel()), f32(lr), f32(b1), f32(b2), f32(eps),
          i32(1 if bias_correction else 0), i64(t), stream())
 

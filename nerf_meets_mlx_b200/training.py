@@ -27,7 +27,7 @@ class NeRFTrainer:
     weights) and skips the re-forward."""
 
     def __init__(self, args=None, device="cuda", near=2.0, far=6.0, shared_adam_state=True,
-                 reuse_coarse_forward=False, process_group=None, max_rays=8192):
+                 reuse_coarse_forward=False, process_group=None, max_rays=8192, use_cuda_graph=False):
         self.args = args if args is not None else default_args(N_importance=128)
         self.device = torch.device(device)
         self.near, self.far = float(near), float(far)
@@ -41,6 +41,13 @@ class NeRFTrainer:
         self.white_bkgd = bool(self.args.white_bkgd)
         self.reuse_coarse_forward = reuse_coarse_forward
         self.iteration = 0
+        # CUDA-graph replay of the iteration (single GPU): the ~70 launches of a step are captured once and replayed,
+        # removing the launch gaps; the learning rate lives in a device scalar so replays follow the decay schedule.
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
+        self._graph_io = None
+        self._lr_dev = None
+        self.graph_launches = 0  # libnmx kernel launches inside one captured iteration
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self._g_coarse = torch.empty_like(self.coarse.flat.data)
@@ -72,12 +79,55 @@ class NeRFTrainer:
         d_raw = ops.composite_bwd(raw.view(B, n, 4), z, rays[:, 3:6].contiguous(), d_rgb, white_bkgd=white_bkgd)
         model._bwd_raw(d_raw.view(B * n, 4), B * n, out=g_buf)
         self._allreduce_mean(g_buf)
-        self.optimizer.update(model, g_buf)
+        self.optimizer.update(model, g_buf, lr_dev=self._lr_dev)
         return loss, weights
 
     def train_iteration(self, rays_o, rays_d, target, u_vals=None):
         """One pass of the reference loop body on this rank's shard of rays.  Returns device scalars."""
+        if self.use_cuda_graph and self.world == 1:
+            return self._train_iteration_graphed(rays_o, rays_d, target, u_vals)
         self.iteration += 1
+        out = self._iteration_body(rays_o, rays_d, target, u_vals)
+        self._advance_lr()
+        return out
+
+    def _advance_lr(self):
+        # learning-rate decay (__test_nerf.py:302-305)
+        decay_steps = self.args.lrate_decay * 1000
+        self.optimizer.learning_rate = self.args.lrate * (0.1 ** (self.iteration / decay_steps))
+
+    def _train_iteration_graphed(self, rays_o, rays_d, target, u_vals):
+        from . import _lib_loader as L
+        if self._lr_dev is None:
+            self._lr_dev = torch.empty((), dtype=torch.float32, device=rays_o.device)
+        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+        key = (tuple(rays_o.shape), u_vals is not None)
+        if self._graph is None or self._graph_io["key"] != key:
+            if self.iteration == 0:  # the very first iteration runs eagerly: it is the warm-up (and a real step)
+                self.iteration += 1
+                out = self._iteration_body(rays_o, rays_d, target, u_vals)
+                self._advance_lr()
+                return out
+            io = {"key": key, "o": rays_o.clone(), "d": rays_d.clone(), "t": target.clone(),
+                  "u": u_vals.clone() if u_vals is not None else None}
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g):
+                io["out"] = self._iteration_body(io["o"], io["d"], io["t"], io["u"])
+            self.graph_launches = L.launch_count() - n0
+            self._graph, self._graph_io = g, io
+        io = self._graph_io
+        io["o"].copy_(rays_o); io["d"].copy_(rays_d); io["t"].copy_(target)
+        if u_vals is not None:
+            io["u"].copy_(u_vals)
+        self.iteration += 1
+        self.optimizer.step_count += 2 if self.fine is not None else 1
+        self._graph.replay()
+        self._advance_lr()
+        return io["out"]
+
+    def _iteration_body(self, rays_o, rays_d, target, u_vals=None):
         rays = assemble_rays(rays_o, rays_d, self.near, self.far)
         B = rays.shape[0]
         rays_d_c = rays[:, 3:6].contiguous()
@@ -95,9 +145,6 @@ class NeRFTrainer:
             loss_f, _ = self._step(self.fine, rays, z_fine, target, False, self._g_fine)  # white_bkgd=False (:106)
             out["loss_fine"] = loss_f
             out["z_fine"] = z_fine
-        # learning-rate decay (__test_nerf.py:302-305)
-        decay_steps = self.args.lrate_decay * 1000
-        self.optimizer.learning_rate = self.args.lrate * (0.1 ** (self.iteration / decay_steps))
         return out
 
     # ------------------------------------------------------------------ inference

@@ -115,3 +115,28 @@ def test_render_api_shapes_and_coarse_fine():
         want = want.numpy()
         err = np.abs(got.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-6)
         assert err < 2e-2, (name, err)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager():
+    """The captured-and-replayed iteration (device-resident learning rate) follows the eager one step for step."""
+    import torch
+    from nerf_meets_mlx_b200.models.NeRF import default_args
+    from nerf_meets_mlx_b200.training import NeRFTrainer
+    B = 256
+    torch.manual_seed(0)
+    data = [(torch.randn(B, 3, device="cuda") * 0.1 + torch.tensor([0.0, 0.0, 4.0], device="cuda"),
+             torch.nn.functional.normalize(torch.randn(B, 3, device="cuda") * 0.2 + torch.tensor([0.0, 0.0, -1.0], device="cuda"), dim=-1),
+             torch.rand(B, 3, device="cuda"), torch.rand(B, 128, device="cuda")) for _ in range(4)]
+    losses = []
+    for graphed in (False, True):
+        tr = NeRFTrainer(default_args(N_importance=128, n_depth_samples=64, lrate_decay=0.001), device="cuda", max_rays=B,
+                         use_cuda_graph=graphed)
+        ls = []
+        for o, d, t, u in data:
+            out = tr.train_iteration(o, d, t, u_vals=u)
+            ls.append((float(out["loss_coarse"]), float(out["loss_fine"])))
+        assert (tr._graph is not None) == graphed
+        losses.append(ls)
+    for (ce, fe), (cg, fg) in zip(*losses):
+        assert abs(ce - cg) <= 2e-3 * abs(ce) and abs(fe - fg) <= 2e-3 * abs(fe), (losses[0], losses[1])
