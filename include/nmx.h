@@ -43,6 +43,16 @@ int nmx_add_noise_z_fwd(const float* z, const float* t_rand, float* z_out, int64
 /* pos = o + z*d (rendering/render.py:142): rays [B, ray_stride] (o at col 0, d at col 3), z [B, n] -> pos [B, n, 3] */
 int nmx_ray_points_fwd(const float* rays, int ray_stride, const float* z, float* pos, int64_t B, int n, void* stream);
 
+/* ---------------------------------------------------------------- ray generation */
+/* get_rays (rendering/ray.py:7-35) + the ray-batch assembly of render() (rendering/render.py:283-328, ndc=False)
+ * and of the training loop (__test_nerf.py:208-236), per pixel id (= row*W + col; pix == NULL -> ids 0..B-1):
+ * rays[b] = [o(3), d(3), near, far, d/||d||(3)] truncated to ray_stride in {6, 8, 11}.  c2w: device [3, >=4] fp32
+ * (row stride c2w_ld).  Pinhole K as doubles: the direction runs in float64 and is cast to fp32, as the reference
+ * does with a float64 K.  Optional target gather: target[b, 0:3] = image[id, 0:3] (image [H*W, img_ld] fp32). */
+int nmx_gen_rays(const float* c2w, int c2w_ld, double fx, double fy, double cx, double cy, int H, int W,
+                 const int32_t* pix, int64_t B, float near, float far, float* rays, int ray_stride,
+                 const float* image, int img_ld, float* target, void* stream);
+
 /* ---------------------------------------------------------------- positional encodings (K2a/K2b) */
 /* Embedder.embed (models/embedding.py:35-71): [x, sin(f0 x), cos(f0 x), ...], f_k = k^2 (reference quirk).
  * x: [P, in_dim] -> out: [P, (include_input?in_dim:0) + 2*in_dim*n_freqs] */
@@ -51,6 +61,10 @@ int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n
  * (dim-major, freq-minor); optional input appended at the end.  bands: [n_freqs] fp32 on device. */
 int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim, int n_freqs,
                           int include_input, void* stream);
+
+/* SphericalHarmonicsEncoding.__call__ (encoding/spherical_harmonics.py:33-94), real SH basis up to degree 4 of the
+ * first three components of dirs [B, in_dim] -> out [B, (n_degrees+1)^2]; fp32, reference evaluation order. */
+int nmx_sh_encode_fwd(const float* dirs, int in_dim, float* out, int64_t B, int n_degrees, void* stream);
 
 /* ---------------------------------------------------------------- multires hash grid (K2c) */
 /* MultiHashEncoding.hash (encoding/multi_hash.py:61-77): coords [M, 3] int32 -> idx [M] int32,

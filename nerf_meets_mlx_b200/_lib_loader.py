@@ -64,6 +64,10 @@ def f32(v):
     return ctypes.c_float(float(v))
 
 
+def f64(v):
+    return ctypes.c_double(float(v))
+
+
 def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -205,3 +205,122 @@ extern "C" int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* 
   NMX_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Spherical-harmonics direction encoding, degree <= 4 (encoding/spherical_harmonics.py:33-94).  One thread per
+// direction; every product / sum is a separately rounded fp32 operation in the reference's evaluation order
+// (Python scalar * fp32 array stays fp32), so the result is bit-comparable with the restated reference.
+__global__ void sh_encode_kernel(const float* __restrict__ dirs, int in_dim, float* __restrict__ out, int64_t B,
+                                 int level) {
+  const int od = (level + 1) * (level + 1);
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < B; p += (int64_t)gridDim.x * blockDim.x) {
+    const float x = dirs[p * in_dim + 0], y = dirs[p * in_dim + 1], z = dirs[p * in_dim + 2];
+#define M_(a, b) __fmul_rn((a), (b))
+#define S_(a, b) __fsub_rn((a), (b))
+#define A_(a, b) __fadd_rn((a), (b))
+    const float xx = M_(x, x), yy = M_(y, y), zz = M_(z, z), xy = M_(x, y), yz = M_(y, z), xz = M_(x, z);
+    float* o = out + p * od;
+    o[0] = 0.28209479177387814f;
+    if (level >= 1) {
+      o[1] = M_(0.4886025119029199f, y);
+      o[2] = M_(0.4886025119029199f, z);
+      o[3] = M_(0.4886025119029199f, x);
+    }
+    if (level >= 2) {
+      o[4] = M_(1.0925484305920792f, xy);
+      o[5] = M_(1.0925484305920792f, yz);
+      o[6] = S_(M_(0.9461746957575601f, zz), 0.31539156525251999f);
+      o[7] = M_(1.0925484305920792f, xz);
+      o[8] = M_(0.5462742152960396f, S_(xx, yy));
+    }
+    if (level >= 3) {
+      const float t3xx_yy = S_(M_(3.f, xx), yy), xx_3yy = S_(xx, M_(3.f, yy));
+      o[9] = M_(M_(0.5900435899266435f, y), t3xx_yy);
+      o[10] = M_(M_(2.890611442640554f, xy), z);
+      o[11] = M_(M_(0.4570457994644658f, y), S_(M_(5.f, zz), 1.f));
+      o[12] = M_(M_(0.3731763325901154f, z), S_(M_(5.f, zz), 3.f));
+      o[13] = M_(M_(0.4570457994644658f, x), S_(M_(5.f, zz), 1.f));
+      o[14] = M_(M_(1.445305721320277f, z), S_(xx, yy));
+      o[15] = M_(M_(0.5900435899266435f, x), xx_3yy);
+      if (level >= 4) {
+        o[16] = M_(M_(2.5033429417967046f, xy), S_(xx, yy));
+        o[17] = M_(M_(1.7701307697799304f, yz), t3xx_yy);
+        o[18] = M_(M_(0.9461746957575601f, xy), S_(M_(7.f, zz), 1.f));
+        o[19] = M_(M_(0.6690465435572892f, yz), S_(M_(7.f, zz), 3.f));
+        o[20] = M_(0.10578554691520431f, A_(S_(M_(M_(35.f, zz), zz), M_(30.f, zz)), 3.f));
+        o[21] = M_(M_(0.6690465435572892f, xz), S_(M_(7.f, zz), 3.f));
+        o[22] = M_(M_(0.47308734787878004f, S_(xx, yy)), S_(M_(7.f, zz), 1.f));
+        o[23] = M_(M_(1.7701307697799304f, xz), xx_3yy);
+        o[24] = M_(0.6258357354491761f, S_(M_(xx, xx_3yy), M_(yy, t3xx_yy)));
+      }
+    }
+#undef M_
+#undef S_
+#undef A_
+  }
+}
+
+extern "C" int nmx_sh_encode_fwd(const float* dirs, int in_dim, float* out, int64_t B, int n_degrees, void* stream) {
+  NMX_CHECK_ARG(B >= 0 && in_dim >= 3 && n_degrees >= 0 && n_degrees <= 4, "B >= 0, in_dim >= 3, 0 <= n_degrees <= 4");
+  if (B == 0) return 0;
+  NMX_CHECK_ARG(dirs && out, "dirs, out non-null");
+  sh_encode_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(dirs, in_dim, out, B, n_degrees);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray generation + ray-batch assembly (rendering/ray.py:7-35, rendering/render.py:283-328 with ndc=False,
+// __test_nerf.py:208-236): pixel id -> [o(3), d(3), near, far, viewdirs(3)] and, optionally, the target pixel.
+// get_rays runs in float64 in the reference when K is a float64 array (NumPy >= 2 promotion) and is cast to fp32
+// afterwards: the same here, with separately rounded products and the sequential 3-term sum NumPy uses.
+__global__ void gen_rays_kernel(const float* __restrict__ c2w, int c2w_ld, double fx, double fy, double cx, double cy,
+                                int W, const int32_t* __restrict__ pix, int64_t B, float near, float far,
+                                float* __restrict__ rays, int ray_stride, const float* __restrict__ image, int img_ld,
+                                float* __restrict__ target) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = pix ? (int64_t)pix[b] : b;
+    const int row = (int)(id / W), col = (int)(id - (int64_t)row * W);
+    const double d0 = __ddiv_rn(__dsub_rn((double)(float)col, cx), fx);
+    const double d1 = -__ddiv_rn(__dsub_rn((double)(float)row, cy), fy);
+    const double d2 = -1.0;
+    float d[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double v = __dadd_rn(__dadd_rn(__dmul_rn(d0, (double)c2w[r * c2w_ld + 0]), __dmul_rn(d1, (double)c2w[r * c2w_ld + 1])),
+                                 __dmul_rn(d2, (double)c2w[r * c2w_ld + 2]));
+      d[r] = (float)v;
+    }
+    float* o = rays + b * ray_stride;
+    o[0] = c2w[0 * c2w_ld + 3];
+    o[1] = c2w[1 * c2w_ld + 3];
+    o[2] = c2w[2 * c2w_ld + 3];
+    o[3] = d[0]; o[4] = d[1]; o[5] = d[2];
+    if (ray_stride >= 8) { o[6] = near; o[7] = far; }
+    if (ray_stride >= 11) {  // viewdirs = d / ||d|| in fp32 (render.py:307)
+      const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+      const float nrm = __fsqrt_rn(n2);
+      o[8] = __fdiv_rn(d[0], nrm); o[9] = __fdiv_rn(d[1], nrm); o[10] = __fdiv_rn(d[2], nrm);
+    }
+    if (target) {
+      const float* px = image + id * img_ld;
+      target[b * 3 + 0] = px[0]; target[b * 3 + 1] = px[1]; target[b * 3 + 2] = px[2];
+    }
+  }
+}
+
+extern "C" int nmx_gen_rays(const float* c2w, int c2w_ld, double fx, double fy, double cx, double cy, int H, int W,
+                            const int32_t* pix, int64_t B, float near, float far, float* rays, int ray_stride,
+                            const float* image, int img_ld, float* target, void* stream) {
+  NMX_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && c2w_ld >= 4 && (ray_stride == 6 || ray_stride == 8 || ray_stride == 11),
+                "B >= 0; H, W >= 1; c2w_ld >= 4; ray_stride in {6, 8, 11}");
+  NMX_CHECK_ARG(fx != 0.0 && fy != 0.0, "focal lengths must be non-zero");
+  NMX_CHECK_ARG((target == nullptr) || (image != nullptr && img_ld >= 3), "target needs image with img_ld >= 3");
+  NMX_CHECK_ARG(pix != nullptr || B <= (int64_t)H * W, "without pixel ids B <= H*W");
+  if (B == 0) return 0;
+  NMX_CHECK_ARG(c2w && rays, "c2w, rays non-null");
+  gen_rays_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(c2w, c2w_ld, fx, fy, cx, cy, W, pix, B, near, far,
+                                                                      rays, ray_stride, image, img_ld, target);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}

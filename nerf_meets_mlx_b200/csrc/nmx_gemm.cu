@@ -325,13 +325,19 @@ struct WgradArgs {
   int n_valid;        // only columns < n_valid are accumulated (padded K inputs)
   float* db;          // optional bias gradient [M_total]: db[m] += sum_p dY[p, m] (ones-column MMA), or null
   int kb_per_cta;     // 64-point blocks per CTA
+  // optional second 64-column operand sharing the SAME dY tile (dY is then read once for both products):
+  // dW2[m, w2_col + n] += sum_p dY[p, m] X2[p, x2_col + n], n < n_valid2
+  int x2_col;
+  float* dW2;
+  int ldw2, w2_col, n_valid2;
 };
 
-template <int STAGES>
+template <int STAGES, bool DUAL>
 struct WgradSmem {
   static constexpr int kABytes = 2 * 64 * 64 * 2;   // two 64(M) x 64(P) boxes
   static constexpr int kBBytes = 4 * 64 * 64 * 2;   // up to four 64(N) x 64(P) boxes
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kB2Bytes = DUAL ? 64 * 64 * 2 : 0;  // one more 64(N2) x 64(P) box of the second operand
+  static constexpr int kStageBytes = kABytes + kBBytes + kB2Bytes;
   static constexpr int kOnesOff = STAGES * kStageBytes;          // constant all-ones 64(N) x 64(P) box for bias grads
   static constexpr int kBarOff = kOnesOff + 8192;
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 1) * 8;
@@ -339,10 +345,13 @@ struct WgradSmem {
   static constexpr int kAlloc = kTotal + 1024;
 };
 
-template <int STAGES>
+template <int STAGES, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs args) {
-  using L = WgradSmem<STAGES>;
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+             const __grid_constant__ CUtensorMap tmX2, const WgradArgs args) {
+  using L = WgradSmem<STAGES, DUAL>;
+  constexpr uint32_t kCol2 = 256;                  // accumulator columns of the second operand (DUAL)
+  constexpr uint32_t kColOnes = DUAL ? 320 : 256;  // accumulator columns of the ones-MMA (bias gradient)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -362,6 +371,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
+    if (DUAL) tma_prefetch_desc(&tmX2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -392,7 +402,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = L::kABytes + (uint32_t)nb * 64 * 64 * 2;
+      const uint32_t tx = L::kABytes + (uint32_t)nb * 64 * 64 * 2 + L::kB2Bytes;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sA = smem + stage * L::kStageBytes;
@@ -402,6 +412,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         tma_load_2d(sA, &tmDY, &full[stage], args.dy_col + m_tile * 128, p);
         tma_load_2d(sA + 8192, &tmDY, &full[stage], args.dy_col + m_tile * 128 + 64, p);
         for (int j = 0; j < nb; ++j) tma_load_2d(sB + j * 8192, &tmX, &full[stage], args.x_col + j * 64, p);
+        if (DUAL) tma_load_2d(sB + L::kBBytes, &tmX2, &full[stage], args.x2_col, p);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -409,6 +420,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
       const uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t idesc2 = make_idesc_bf16(128, 64, 1, 1);
       const uint64_t odesc = make_smem_desc(smem_u32(smem + L::kOnesOff), 8192, 1024);
       int stage = 0;
       uint32_t phase = 0;
@@ -420,11 +432,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         // MN-major SW128: LBO = 8192 B between 64-wide M/N atoms (separate TMA boxes), SBO = 1024 B per 8 points
         const uint64_t adesc = make_smem_desc(a_addr, 8192, 1024);
         const uint64_t bdesc = make_smem_desc(b_addr, 8192, 1024);
+        const uint64_t b2desc = make_smem_desc(b_addr + L::kBBytes, 8192, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // 16 points = 16 rows of 128 B = 2048 B -> +128 in the (addr >> 4) field
           umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
-          if (want_db) umma_bf16(tmem_base + 256, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
+          if (DUAL) umma_bf16(tmem_base + kCol2, adesc + (uint64_t)(k * 128), b2desc + (uint64_t)(k * 128), idesc2, (kb | k) != 0);
+          if (want_db) umma_bf16(tmem_base + kColOnes, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
         }
         umma_commit(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -436,33 +450,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     mbar_wait(tfull, 0);
     tc_fence_after();
     const int m = m_tile * 128 + q * 32 + lane;
-    float* wrow = args.dW + (size_t)m * args.ldw + args.w_col;
     // flush: one vector reduction (red.global.add.v4.f32, 16 B) per 4 columns when the row start is 16 B aligned --
     // 4x fewer L2 atomic operations than scalar adds; the scalar path handles odd leading dimensions (63 / 283 / 319)
-    const bool vec_ok = ((args.ldw & 3) == 0) && ((args.w_col & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(args.dW) & 15) == 0);
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + c0 + ((uint32_t)(q * 32) << 16), r);
-      tmem_ld_wait();
-      if (m < args.M) {
-        if (vec_ok && c0 + 32 <= args.n_valid) {
+    auto flush = [&](uint32_t tcol0, int ncols, float* dW, int ldw, int w_col, int n_valid) {
+      float* wrow = dW + (size_t)m * ldw + w_col;
+      const bool vec_ok = ((ldw & 3) == 0) && ((w_col & 3) == 0) && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + tcol0 + c0 + ((uint32_t)(q * 32) << 16), r);
+        tmem_ld_wait();
+        if (m < args.M) {
+          if (vec_ok && c0 + 32 <= n_valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c0 + j),
-                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
-                         "f"(__uint_as_float(r[j + 3]))
-                         : "memory");
-        } else {
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c0 + j),
+                           "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                           "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < args.n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < n_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+          }
         }
       }
-    }
+    };
+    flush(0, N, args.dW, args.ldw, args.w_col, args.n_valid);
+    if (DUAL) flush(kCol2, 64, args.dW2, args.ldw2, args.w2_col, args.n_valid2);
     if (want_db) {
       uint32_t r[16];
-      tmem_ld_32x16(tmem_base + 256 + ((uint32_t)(q * 32) << 16), r);
+      tmem_ld_32x16(tmem_base + kColOnes + ((uint32_t)(q * 32) << 16), r);
       tmem_ld_wait();
       if (m < args.M) atomicAdd(args.db + m, __uint_as_float(r[0]));
     }
@@ -575,14 +592,22 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
 int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   if (g.P <= 0) return 0;
   if (g.M % 64 || g.M <= 0 || g.N % 64 || g.N > 256 || g.N <= 0) { set_error("wgrad: M %% 64, N %% 64, N <= 256 required (M=%d N=%d)", g.M, g.N); return NMX_E_BADARG; }
-  CUtensorMap tDY, tX;
+  const bool dual = g.X2 != nullptr;
+  if (dual && (g.dW2 == nullptr || g.n_valid2 <= 0 || g.n_valid2 > 64)) { set_error("wgrad: second operand needs dW2 and 0 < n_valid2 <= 64"); return NMX_E_BADARG; }
+  CUtensorMap tDY, tX, tX2;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tDY, g.dY, g.P, g.dy_cols, g.dy_ld, 64))) return rc;
   if ((rc = make_tmap_bf16_2d(&tX, g.X, g.P, g.x_cols, g.x_ld, 64))) return rc;
+  if (dual) {
+    if ((rc = make_tmap_bf16_2d(&tX2, g.X2, g.P, g.x2_cols, g.x2_ld, 64))) return rc;
+  } else {
+    tX2 = tX;
+  }
   WgradArgs a;
   a.dy_col = g.dy_col; a.x_col = g.x_col; a.P = (int)g.P; a.M = g.M; a.N = g.N; a.dW = g.dW; a.ldw = g.ldw; a.w_col = g.w_col;
   a.n_valid = g.n_valid > 0 ? g.n_valid : g.N;
   a.db = g.db;
+  a.x2_col = g.x2_col; a.dW2 = g.dW2; a.ldw2 = g.ldw2; a.w2_col = g.w2_col; a.n_valid2 = g.n_valid2;
   int m_tiles = (g.M + 127) / 128;
   int total_kb = (int)((g.P + 63) / 64);
   const int cta_cap = (g.max_ctas > 0 && g.max_ctas < kNumSMs) ? g.max_ctas : kNumSMs;
@@ -591,11 +616,18 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   if (splits > total_kb) splits = total_kb;
   a.kb_per_cta = (total_kb + splits - 1) / splits;
   splits = (total_kb + a.kb_per_cta - 1) / a.kb_per_cta;
-  using L = WgradSmem<4>;
-  static bool attr = false;
-  if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
-  prof_begin(1, 2.0 * (double)g.P * g.M * g.N, stream);
-  wgrad_kernel<4><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, a);
+  prof_begin(1, 2.0 * (double)g.P * g.M * (g.N + (dual ? 64 : 0)), stream);
+  if (dual) {
+    using L = WgradSmem<3, true>;
+    static bool attr = false;
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    wgrad_kernel<3, true><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, tX2, a);
+  } else {
+    using L = WgradSmem<4, false>;
+    static bool attr = false;
+    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    wgrad_kernel<4, false><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, tX2, a);
+  }
   prof_end(stream);
   NMX_LAUNCH_CHECK();
   return 0;

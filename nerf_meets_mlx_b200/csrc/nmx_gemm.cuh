@@ -25,6 +25,10 @@ struct WgradDesc {
   float* dW; int ldw, w_col; int n_valid;             // only columns < n_valid are accumulated
   float* db;                                          // optional: db[m] += sum_p dY[p, m] (bias gradient), or null
   int max_ctas;                                       // 0 = all SMs; else cap on the CTA count (concurrent kernels)
+  // optional second operand (64 columns of X2 from x2_col) contracted with the same dY in the same pass:
+  // dW2[m, w2_col + n] += sum_p dY[p, m] X2[p, x2_col + n] for n < n_valid2 (<= 64)
+  const void* X2; int x2_cols, x2_ld, x2_col;
+  float* dW2; int ldw2, w2_col, n_valid2;
 };
 
 // live profiling hooks (nmx_profile_enable): kind 0 layer GEMM, 1 wgrad, 2 chain forward (inference), 3 chain forward

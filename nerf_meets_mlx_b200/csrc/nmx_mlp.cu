@@ -992,8 +992,25 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
       float* dWd = d_params + p->dir.w_off;
       float* gfold = (float*)(c.act + c.al.gfold);  // G = d_hd^T h_{D-1} (+ db_dir = column sums of d_hd)
       if (k == 0) NMX_CUDA(cudaMemsetAsync(gfold, 0, (size_t)(W / 2) * W * sizeof(float), sw));
-      if ((rc = wg(c.GHD(), W / 2, hl, W, 0, W / 2, W, W, gfold, W, 0, d_params + p->dir.b_off))) return rc;
-      if ((rc = wg(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
+      // one pass over d_hd for both products: G (with h_{D-1}) and the dir-PE columns of dW_dir (second operand)
+      auto wg2 = [&](const bf16* dY, int dy_cols, const bf16* X, int M, float* dW, int ldw, int w_col, float* db,
+                     int x2_col, int n_valid2, float* dW2, int ldw2, int w2_col) {
+        WgradDesc g{};
+        g.dY = dY + r0 * dy_cols; g.dy_cols = dy_cols; g.dy_ld = dy_cols; g.dy_col = 0;
+        g.X = X + r0 * W; g.x_cols = W; g.x_ld = W; g.x_col = 0;
+        g.P = rows; g.M = M; g.N = W; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = W; g.db = db;
+        g.X2 = c.X0() + r0 * p->x0_cols; g.x2_cols = p->x0_cols; g.x2_ld = p->x0_cols; g.x2_col = x2_col;
+        g.dW2 = dW2; g.ldw2 = ldw2; g.w2_col = w2_col; g.n_valid2 = n_valid2;
+        g.max_ctas = wg_ctas;
+        return launch_wgrad(g, sw);
+      };
+      const bool dual_ok = (W == 256) && p->dir_pad == 64 && p->pos_pad == 64 && !getenv("NMX_DISABLE_DUAL_WGRAD");
+      if (dual_ok) {
+        if ((rc = wg2(c.GHD(), W / 2, hl, W / 2, gfold, W, 0, d_params + p->dir.b_off, p->pos_pad, p->in_dir, dWd, p->dir.in, W))) return rc;
+      } else {
+        if ((rc = wg(c.GHD(), W / 2, hl, W, 0, W / 2, W, W, gfold, W, 0, d_params + p->dir.b_off))) return rc;
+        if ((rc = wg(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
+      }
       for (int l = p->D - 1; l >= 0; --l) {
         const LinearRef& r = p->trunk[l];
         const bf16* dY = c.G(l);
@@ -1002,6 +1019,8 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
         const bool skip_in = (r.in == W + p->in_pos);
         if (l == 0) {
           if ((rc = wg(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, db))) return rc;
+        } else if (skip_in && dual_ok) {  // skip layer: [x_pos | h] operands against one read of dY
+          if ((rc = wg2(dY, W, c.H(l - 1), W, dW, r.in, p->in_pos, db, 0, p->in_pos, dW, r.in, 0))) return rc;
         } else if (skip_in) {
           if ((rc = wg(dY, W, c.X0(), p->x0_cols, 0, W, p->pos_pad, p->in_pos, dW, r.in, 0, nullptr))) return rc;
           if ((rc = wg(dY, W, c.H(l - 1), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;

@@ -1,4 +1,4 @@
-"""Mirror of mlx_nerf/encoding/__init__.py: `Encoding` base (encoding/__init__.py:10-24) + the two hot-path encoders."""
+"""Mirror of mlx_nerf/encoding/__init__.py: `Encoding` base (encoding/__init__.py:10-24) + the encoders."""
 from abc import abstractmethod
 
 import torch
@@ -20,3 +20,5 @@ class Encoding(torch.nn.Module):
 
 from .sinusoidal import SinusoidalEncoding  # noqa: E402,F401
 from .multi_hash import MultiHashEncoding  # noqa: E402,F401
+from .spherical_harmonics import SphericalHarmonicsEncoding  # noqa: E402,F401
+from .identity import IdentityEncoding  # noqa: E402,F401

@@ -3,7 +3,7 @@ current CUDA stream.  No CPU path exists; every function raises if the extension
 contiguous CUDA tensors."""
 import torch
 
-from ._lib_loader import NmxError, call, f32, i32, i64, ptr, require_cuda, stream
+from .._lib_loader import NmxError, call, f32, f64, i32, i64, ptr, require_cuda, stream
 
 
 def _f32c(t):
@@ -42,6 +42,33 @@ def ray_points(rays, z):
     return pos
 
 
+def gen_rays(H, W, K, c2w, pix=None, near=0.0, far=1.0, n_cols=11, image=None):
+    """Pixel ids -> ray batch [B, n_cols] (o, d, near, far, viewdirs) and, with `image` [H*W, C>=3], the target
+    pixels [B, 3] (ray.py:7-35 + render.py:283-328 / __test_nerf.py:208-236)."""
+    import numpy as np
+    c2w = torch.as_tensor(np.asarray(c2w, dtype=np.float32) if not isinstance(c2w, torch.Tensor) else c2w)
+    c2w = _f32c(c2w.to("cuda") if not c2w.is_cuda else c2w)
+    if c2w.ndim != 2 or c2w.shape[0] < 3 or c2w.shape[1] < 4:
+        raise ValueError("c2w must be [3|4, 4]")
+    B = H * W if pix is None else int(pix.numel())
+    if pix is not None:
+        pix = pix.to(device=c2w.device, dtype=torch.int32).contiguous()
+    rays = torch.empty((B, n_cols), dtype=torch.float32, device=c2w.device)
+    target = None
+    img_ld = 0
+    if image is not None:
+        image = _f32c(image)
+        require_cuda(image)
+        img_ld = image.shape[-1]
+        if image.numel() != H * W * img_ld:
+            raise ValueError("image must be [H*W, C]")
+        target = torch.empty((B, 3), dtype=torch.float32, device=c2w.device)
+    call("nmx_gen_rays", ptr(c2w), i32(c2w.stride(0)), f64(K[0][0]), f64(K[1][1]), f64(K[0][2]), f64(K[1][2]),
+         i32(H), i32(W), ptr(pix), i64(B), f32(near), f32(far), ptr(rays), i32(n_cols), ptr(image), i32(img_ld),
+         ptr(target), stream())
+    return rays if image is None else (rays, target)
+
+
 # ----------------------------------------------------------------------------------------- encodings
 def pe_embedder(x, n_freqs, include_input=True):
     x = _f32c(x)
@@ -64,6 +91,17 @@ def pe_sinusoidal(x, bands, include_input=False):
     out = torch.empty((P, out_dim), dtype=torch.float32, device=x.device)
     call("nmx_pe_sinusoidal_fwd", ptr(x), ptr(bands), ptr(out), i64(P), i32(in_dim), i32(nf), i32(1 if include_input else 0), stream())
     return out
+
+
+def sh_encode(dirs, n_degrees):
+    d = _f32c(dirs)
+    require_cuda(d)
+    in_dim = d.shape[-1]
+    B = d.numel() // in_dim
+    od = (n_degrees + 1) ** 2
+    out = torch.empty((B, od), dtype=torch.float32, device=d.device)
+    call("nmx_sh_encode_fwd", ptr(d), i32(in_dim), ptr(out), i64(B), i32(n_degrees), stream())
+    return out.reshape(*d.shape[:-1], od)
 
 
 def hashgrid_hash(coords, log2_T):

@@ -1,21 +1,19 @@
-"""Mirror of mlx_nerf/rendering/ray.py (camera -> rays).  O(rays) elementwise prep that feeds the hot path; kept as
-torch ops on the device so no host round trip precedes the kernels."""
+"""Mirror of mlx_nerf/rendering/ray.py (camera -> rays).  O(rays) elementwise prep that feeds the hot path; on the
+device so no host round trip precedes the kernels."""
 import numpy as np
 import torch
 
+from .. import ops
+
 
 def get_rays(H: int, W: int, K, c2w, device=None):
-    """get_rays (rendering/ray.py:7-35): pinhole rays; returns (rays_o, rays_d) [H, W, 3]."""
+    """get_rays (rendering/ray.py:7-35): pinhole rays; returns (rays_o, rays_d) [H, W, 3] (nmx_gen_rays; the direction
+    is evaluated in float64 and cast to fp32, which is what the reference does with its float64 K)."""
     if device is None:
-        device = c2w.device if isinstance(c2w, torch.Tensor) else "cuda"
-    c2w = torch.as_tensor(np.asarray(c2w) if not isinstance(c2w, torch.Tensor) else c2w).to(device=device, dtype=torch.float32)
-    i, j = torch.meshgrid(torch.arange(W, dtype=torch.float32, device=device),
-                          torch.arange(H, dtype=torch.float32, device=device), indexing="xy")
-    fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
-    dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], dim=-1)
-    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], dim=-1)
-    rays_o = c2w[:3, -1].expand(rays_d.shape)
-    return rays_o, rays_d
+        device = c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda else "cuda"
+    c2w = torch.as_tensor(np.asarray(c2w, dtype=np.float32) if not isinstance(c2w, torch.Tensor) else c2w)
+    rays = ops.gen_rays(H, W, K, c2w.to(device=device, dtype=torch.float32), None, 0.0, 1.0, 6)
+    return rays[:, 0:3].reshape(H, W, 3), rays[:, 3:6].reshape(H, W, 3)
 
 
 def ndc_rays(H, W, focal, near, rays_o, rays_d):

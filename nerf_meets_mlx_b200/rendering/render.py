@@ -140,6 +140,10 @@ def batchify_rays(rays_linear, chunk=1024 * 32, **kwargs):
 
 def build_rays(H, W, K, c2w, near, far, use_viewdirs=False, ndc=False, c2w_staticcam=None, rays=None, device="cuda"):
     """Ray assembly of render() (rendering/render.py:283-328): [o, d, near, far (, viewdirs)] fp32 [H*W, 8|11]."""
+    if c2w is not None and not ndc and c2w_staticcam is None:
+        # the case every caller uses (NeRF.py:146-148): one kernel from (K, c2w) to the assembled ray buffer
+        rays_linear = ops.gen_rays(H, W, K, torch.as_tensor(c2w).to(device), None, near, far, 11 if use_viewdirs else 8)
+        return rays_linear, (H, W, 3)
     if c2w is None and rays is not None:
         rays_o, rays_d = rays
     else:

@@ -91,6 +91,13 @@ class NeRFTrainer:
         self._advance_lr()
         return out
 
+    def train_iteration_pixels(self, H, W, K, c2w, pix, image, u_vals=None):
+        """The reference's per-iteration ray selection (__test_nerf.py:208-236) on the device: pixel ids (row*W + col)
+        of one training view -> rays and target pixels in one kernel (nmx_gen_rays), then `train_iteration`.
+        `image` is the view's [H*W, C>=3] fp32 pixels already resident in HBM; no host round trip."""
+        rays, target = ops.gen_rays(H, W, K, c2w, pix, self.near, self.far, 6, image=image)
+        return self.train_iteration(rays[:, 0:3], rays[:, 3:6], target, u_vals)
+
     def _advance_lr(self):
         # learning-rate decay (__test_nerf.py:302-305)
         decay_steps = self.args.lrate_decay * 1000

@@ -2,7 +2,8 @@
 
 Follows mlx_nerf/models/embedding.py:4-90 (PE flavour A, volume path),
 mlx_nerf/encoding/sinusoidal.py:13-66 (PE flavour B, image path) and
-mlx_nerf/encoding/multi_hash.py:13-137 (hash grid, canonical semantics of SURVEY 8a row 9).
+mlx_nerf/encoding/multi_hash.py:13-137 (hash grid, canonical semantics of SURVEY 8a row 9),
+mlx_nerf/encoding/spherical_harmonics.py:13-94 and mlx_nerf/encoding/identity.py:13-32.
 """
 import math
 
@@ -166,3 +167,55 @@ def hashgrid_backward(x, d_out, n_levels, n_feat, scaled_res, log2_T):
         for l in range(n_levels):
             np.add.at(g[l], idx[:, l, k], w[:, l, None] * d[:, l, :])
     return g
+
+
+# ----------------------------------------------------------------------------- SH / identity
+def sh_out_dim(n_degrees):
+    """spherical_harmonics.py:28-31."""
+    return (n_degrees + 1) ** 2
+
+
+def sh_encode(dirs, n_degrees):
+    """spherical_harmonics.py:33-94: real SH basis (r = 1) of the first three components, fp32, Python scalars stay
+    weak (fp32 products), evaluation order as written."""
+    assert 0 <= n_degrees <= 4
+    d = np.asarray(dirs, dtype=F32)
+    x, y, z = d[..., 0], d[..., 1], d[..., 2]
+    xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+    out = np.zeros((*d.shape[:-1], sh_out_dim(n_degrees)), dtype=F32)
+    c = lambda v: F32(v)
+    out[..., 0] = c(0.28209479177387814)
+    if n_degrees >= 1:
+        out[..., 1] = c(0.4886025119029199) * y
+        out[..., 2] = c(0.4886025119029199) * z
+        out[..., 3] = c(0.4886025119029199) * x
+    if n_degrees >= 2:
+        out[..., 4] = c(1.0925484305920792) * xy
+        out[..., 5] = c(1.0925484305920792) * yz
+        out[..., 6] = c(0.9461746957575601) * zz - c(0.31539156525251999)
+        out[..., 7] = c(1.0925484305920792) * xz
+        out[..., 8] = c(0.5462742152960396) * (xx - yy)
+    if n_degrees >= 3:
+        out[..., 9] = c(0.5900435899266435) * y * (c(3) * xx - yy)
+        out[..., 10] = c(2.890611442640554) * xy * z
+        out[..., 11] = c(0.4570457994644658) * y * (c(5) * zz - c(1))
+        out[..., 12] = c(0.3731763325901154) * z * (c(5) * zz - c(3))
+        out[..., 13] = c(0.4570457994644658) * x * (c(5) * zz - c(1))
+        out[..., 14] = c(1.445305721320277) * z * (xx - yy)
+        out[..., 15] = c(0.5900435899266435) * x * (xx - c(3) * yy)
+    if n_degrees >= 4:
+        out[..., 16] = c(2.5033429417967046) * xy * (xx - yy)
+        out[..., 17] = c(1.7701307697799304) * yz * (c(3) * xx - yy)
+        out[..., 18] = c(0.9461746957575601) * xy * (c(7) * zz - c(1))
+        out[..., 19] = c(0.6690465435572892) * yz * (c(7) * zz - c(3))
+        out[..., 20] = c(0.10578554691520431) * (c(35) * zz * zz - c(30) * zz + c(3))
+        out[..., 21] = c(0.6690465435572892) * xz * (c(7) * zz - c(3))
+        out[..., 22] = c(0.47308734787878004) * (xx - yy) * (c(7) * zz - c(1))
+        out[..., 23] = c(1.7701307697799304) * xz * (xx - c(3) * yy)
+        out[..., 24] = c(0.6258357354491761) * (xx * (xx - c(3) * yy) - yy * (c(3) * xx - yy))
+    return out
+
+
+def identity_encode(x):
+    """identity.py:26-31."""
+    return x

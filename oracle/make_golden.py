@@ -19,6 +19,29 @@ REF = os.environ.get("NMX_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def make_tiny_scene(scene, rng):
+    """A 3-split Blender-format scene of 8x8 RGBA frames (deterministic), written once and committed."""
+    import json
+    from PIL import Image
+    if os.path.exists(os.path.join(scene, "transforms_train.json")):
+        return
+    for split, n in (("train", 3), ("val", 2), ("test", 4)):
+        os.makedirs(os.path.join(scene, split), exist_ok=True)
+        frames = []
+        for i in range(n):
+            px = rng.integers(0, 256, size=(8, 8, 4), dtype=np.uint8)
+            px[:2, :, 3] = 0      # fully transparent rows (white-background compositing path)
+            px[2:4, :, 3] = 255
+            Image.fromarray(px, "RGBA").save(os.path.join(scene, split, f"r_{i}.png"))
+            th = float(rng.uniform(-180, 180))
+            c, s_ = float(np.cos(np.deg2rad(th))), float(np.sin(np.deg2rad(th)))
+            frames.append({"file_path": f"./{split}/r_{i}", "rotation": 0.1,
+                           "transform_matrix": [[c, -s_, 0.0, 4.0 * s_], [s_, c, 0.0, -4.0 * c], [0.0, 0.0, 1.0, 0.5 * i],
+                                                [0.0, 0.0, 0.0, 1.0]]})
+        with open(os.path.join(scene, f"transforms_{split}.json"), "w") as fp:
+            json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, fp, indent=1)
+
+
 def main():
     sys.path.insert(0, os.path.join(HERE, "mlx_shim"))
     sys.path.insert(0, REF)
@@ -167,6 +190,60 @@ def main():
     c2w = np.asarray(pose.pose_spherical(30.0, -30.0, 4.0))
     ro, rd = ray.get_rays(H, W, K, c2w[:3, :4])
     np.savez_compressed(os.path.join(OUT, "rays.npz"), K=K, c2w=c2w, rays_o=np.array(ro), rays_d=np.array(rd), H=H, W=W)
+
+    # ---- render() incl. its ray assembly (render.py:268-345: get_rays, viewdir normalisation, near/far columns)
+    mnn.seed(13)
+    net_w = RN.NeRF(n_layers=8, width_layers=128, channel_input=63, channel_input_views=27, channel_output=5,
+                    list_skip_connection_layers=[4], is_use_view_directions=True)  # 128: narrowest view-dir net the CUDA path takes
+    rk = dict(network_query_fn=qf, network_coarse=net_w, n_depth_samples=16, white_bkgd=True, retraw=True,
+              render_rays_func=render.render_rays)
+    r3 = render.render(H, W, K, chunk=20, c2w=c2w[:3, :4], ndc=False, near=2.0, far=6.0, use_viewdirs=True, **rk)
+    g = {}
+    dump_params(net_w, "w/", g)
+    np.savez_compressed(os.path.join(OUT, "render_full.npz"), K=K, c2w=c2w, H=H, W=W, rgb=r3[0], disp=r3[1], acc=r3[2],
+                        **{f"x_{k}": v for k, v in r3[3].items()}, **g)
+
+    # ---- SphericalHarmonicsEncoding / IdentityEncoding (encoding/spherical_harmonics.py, identity.py)
+    from mlx_nerf.encoding.spherical_harmonics import SphericalHarmonicsEncoding
+    from mlx_nerf.encoding.identity import IdentityEncoding
+    dsh = rng.standard_normal(size=(64, 3)).astype(np.float32)
+    dsh /= np.linalg.norm(dsh, axis=-1, keepdims=True)
+    dsh[0] = [0, 0, 1]
+    dsh[1] = [1, 0, 0]
+    dsh[2] = [0, -1, 0]
+    g = {"dirs": dsh, "identity": IdentityEncoding(3)(dsh), "identity_dim": IdentityEncoding(3).get_out_dim()}
+    for lv in range(5):
+        enc = SphericalHarmonicsEncoding(3, lv)
+        g[f"sh_{lv}"] = enc(dsh)
+        g[f"sh_dim_{lv}"] = enc.get_out_dim()
+    np.savez_compressed(os.path.join(OUT, "sh.npz"), **g)
+
+    # ---- metrics (ops/metric.py:12-18)
+    from mlx_nerf.ops import metric
+    pa = rng.random(size=(9, 7, 3)).astype(np.float32)
+    pb = rng.random(size=(9, 7, 3)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "metric.npz"), pred=pa, gt=pb, mse=np.asarray(metric.MSE()(pa, pb)),
+                        psnr=np.asarray(metric.PSNR()(pa, pb)))
+
+    # ---- Blender loader (dataset/dataloader.py:20-113) on the tiny committed scene tests/golden/blender_tiny.
+    # imageio / matplotlib are not in this image: imageio.v2.imread is stood in by PIL (same uint8 array), pyplot by
+    # an empty module (only validate_dataset, a plotting helper, touches it).
+    import types
+    from PIL import Image
+    scene = os.path.join(OUT, "blender_tiny")
+    make_tiny_scene(scene, np.random.default_rng(5))
+    im_mod, im_v2, mpl, plt = (types.ModuleType(n) for n in ("imageio", "imageio.v2", "matplotlib", "matplotlib.pyplot"))
+    im_v2.imread = lambda f: np.asarray(Image.open(f))
+    im_mod.v2 = im_v2
+    mpl.pyplot = plt
+    sys.modules.update({"imageio": im_mod, "imageio.v2": im_v2, "matplotlib": mpl, "matplotlib.pyplot": plt})
+    from mlx_nerf.dataset import dataloader
+    imgs, poses, render_poses, hwf, i_split = dataloader.load_blender_data(scene, half_res=False, testskip=2)
+    i_tr, i_va, i_te, nr, fr, im_w = dataloader.post_load_blender_data(i_split, imgs, True)
+    _, _, _, _, _, im_b = dataloader.post_load_blender_data(i_split, imgs, False)
+    np.savez_compressed(os.path.join(OUT, "blender_loader.npz"), imgs=imgs, poses=poses, render_poses=np.asarray(render_poses),
+                        hwf=np.asarray(hwf, dtype=np.float64), i_train=i_tr, i_val=i_va, i_test=i_te, near=nr, far=fr,
+                        images_white=im_w, images_black=im_b)
     print("golden vectors written to", OUT)
 
 

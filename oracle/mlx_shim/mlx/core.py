@@ -125,6 +125,10 @@ def log(a):
     return _c(_np.log(_np.asarray(a, dtype=_np.float32)))
 
 
+def log10(a):
+    return _c(_np.log10(_np.asarray(a, dtype=_np.float32)))
+
+
 def sin(a):
     return _c(_np.sin(_c(a)))
 

@@ -119,3 +119,14 @@ def image_step(model, opt, X_int, y, n_freqs=10, min_exp=0.0, max_exp=8.0):
 def psnr(mse):
     """ops/metric.py:16-18: 10 log10(1/MSE)."""
     return 10.0 * np.log10(1.0 / mse)
+
+
+def metric_mse(pred, gt):
+    """ops/metric.py:12-14 (fp32 mean of squared differences)."""
+    pred, gt = np.asarray(pred, dtype=np.float32), np.asarray(gt, dtype=np.float32)
+    return np.mean((pred - gt) ** 2, dtype=np.float32)
+
+
+def metric_psnr(pred, gt):
+    """ops/metric.py:16-18."""
+    return np.float32(10) * np.log10(np.float32(1) / metric_mse(pred, gt))

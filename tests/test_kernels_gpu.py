@@ -226,3 +226,70 @@ def test_mse_adam(ops):
     np.testing.assert_allclose(M.cpu().numpy(), m2, rtol=1e-5, atol=2e-7)  # fma contraction vs numpy
     np.testing.assert_allclose(V.cpu().numpy(), v2, rtol=1e-5, atol=2e-7)
     np.testing.assert_allclose(W.cpu().numpy(), w - 5e-4 * m2 / (np.sqrt(v2) + 1e-8), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ ray generation, SH, metrics
+def test_gen_rays_golden_bit_exact(ops, golden):
+    """nmx_gen_rays against the reference's own get_rays output (bit-exact o, d) and the restated ray assembly."""
+    g, gf = golden("rays"), golden("render_full")
+    H, W = int(g["H"]), int(g["W"])
+    from nerf_meets_mlx_b200.rendering import ray
+    ro, rd = ray.get_rays(H, W, g["K"], g["c2w"][:3, :4])
+    np.testing.assert_array_equal(ro.cpu().numpy(), g["rays_o"].astype(np.float32))
+    np.testing.assert_array_equal(rd.cpu().numpy(), g["rays_d"].astype(np.float32))
+    rays = ops.gen_rays(H, W, gf["K"], gf["c2w"], None, 2.0, 6.0, 11).cpu().numpy()
+    ref = orend.build_rays(H, W, gf["K"], gf["c2w"][:3, :4], 2.0, 6.0, use_viewdirs=True)
+    np.testing.assert_array_equal(rays[:, :8], ref[:, :8])
+    np.testing.assert_allclose(rays[:, 8:], ref[:, 8:], rtol=0, atol=1.2e-7)
+
+
+def test_gen_rays_pixel_selection_and_targets(ops):
+    """The training loop's ray selection (__test_nerf.py:208-236): random pixel ids of a 400x400 view, rays + targets."""
+    rng = np.random.default_rng(3)
+    H = W = 400
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    c2w = orend.pose_spherical(77.0, -30.0, 4.0)
+    img = rng.random(size=(H * W, 4)).astype(np.float32)
+    pix = rng.choice(H * W, size=4096, replace=False).astype(np.int32)
+    rays, tgt = ops.gen_rays(H, W, K, c2w, torch.from_numpy(pix).cuda(), 2.0, 6.0, 11, image=dev(img))
+    ro, rd = orend.get_rays(H, W, K, c2w[:3, :4])
+    sel_o = np.reshape(ro, (-1, 3))[pix].astype(np.float32)
+    sel_d = np.reshape(rd, (-1, 3))[pix].astype(np.float32)
+    rays = rays.cpu().numpy()
+    np.testing.assert_array_equal(rays[:, 0:3], sel_o)
+    np.testing.assert_array_equal(rays[:, 3:6], sel_d)
+    np.testing.assert_array_equal(rays[:, 6:8], np.tile(np.array([[2.0, 6.0]], np.float32), (4096, 1)))
+    vd = sel_d / np.sqrt(np.sum(sel_d * sel_d, -1, keepdims=True))
+    np.testing.assert_allclose(rays[:, 8:11], vd, rtol=0, atol=1.2e-7)
+    np.testing.assert_array_equal(tgt.cpu().numpy(), img[pix, :3])
+    # empty batch and bad arguments
+    assert ops.gen_rays(H, W, K, c2w, torch.zeros(0, dtype=torch.int32, device="cuda"), 2.0, 6.0, 11).shape == (0, 11)
+    with pytest.raises(RuntimeError):
+        ops.gen_rays(H, W, K, c2w, None, 2.0, 6.0, 7)
+
+
+def test_sh_encoding_golden_bit_exact(ops, golden):
+    from nerf_meets_mlx_b200.encoding import SphericalHarmonicsEncoding, IdentityEncoding
+    g = golden("sh")
+    d = dev(g["dirs"])
+    for lv in range(5):
+        enc = SphericalHarmonicsEncoding(3, lv)
+        assert enc.get_out_dim() == int(g[f"sh_dim_{lv}"])
+        np.testing.assert_array_equal(enc(d).cpu().numpy(), g[f"sh_{lv}"])
+    with pytest.raises(AssertionError):
+        SphericalHarmonicsEncoding(3, 5)
+    big = torch.nn.functional.normalize(torch.randn(100_003, 3, device="cuda"), dim=-1)
+    np.testing.assert_array_equal(ops.sh_encode(big, 4).cpu().numpy(), oenc.sh_encode(big.cpu().numpy(), 4))
+    ident = IdentityEncoding(3)
+    assert ident.get_out_dim() == 3 and ident(d) is d
+    assert ops.sh_encode(big[:0], 4).shape == (0, 25)
+
+
+def test_metric_mirror(golden):
+    from nerf_meets_mlx_b200.ops import metric
+    g = golden("metric")
+    np.testing.assert_allclose(float(metric.MSE()(dev(g["pred"]), dev(g["gt"]))), float(g["mse"]), rtol=2e-6)
+    np.testing.assert_allclose(float(metric.PSNR()(dev(g["pred"]), dev(g["gt"]))), float(g["psnr"]), rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        metric.SSIM()(dev(g["pred"]), dev(g["gt"]))
