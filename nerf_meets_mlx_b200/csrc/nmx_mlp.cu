@@ -279,70 +279,82 @@ head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
 // backward of a small head: d_out[p, col0 + o] given.
 //   dW[o, k] += sum_p d_out[p,o] h[p,k] ; db[o] += sum_p d_out[p,o]
 //   optionally d_h[p, k] = (sum_o d_out[p,o] W[o,k]) * (h[p,k] > 0)   (bf16; when the head input is post-ReLU)
-// One warp per point per iteration: lane l owns CPL = K/32 adjacent columns (one 4/8/16 B vector load of the bf16 row,
-// a coalesced 2*K-byte warp transaction), keeps its dW partials in registers over the whole point loop, and the block
-// reduces them through shared memory into ONE set of atomics.
-template <int CPL, int NOUT>
+// Every lane loads 16 B (8 bf16 columns) of a point's row, so a point takes K/8 lanes and a warp iteration covers
+// 256/K points with one fully coalesced 512 B transaction; the dW partials stay in registers over the whole point loop
+// as packed fp32 pairs (fma.rn.f32x2), and the block reduces them through shared memory into ONE set of atomics.
+template <int K, int NOUT, bool HAS_DH>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ Wt, const float* __restrict__ d_out,
                 int ldo, int col0, int64_t P, float* __restrict__ dW, float* __restrict__ db, bf16* __restrict__ d_h,
                 int ldd) {
-  constexpr int K = CPL * 32;
+  constexpr int LPP = K / 8;     // lanes per point
+  constexpr int PPW = 32 / LPP;  // points per warp iteration
   __shared__ float s_acc[NOUT * K + NOUT];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
+  const int sub = lane / LPP, cl = lane % LPP;
   for (int i = threadIdx.x; i < NOUT * K + NOUT; i += blockDim.x) s_acc[i] = 0.0f;
   __syncthreads();
-  float w[NOUT][CPL], acc[NOUT][CPL], accb[NOUT];
+  float w[HAS_DH ? NOUT : 1][8];
+  uint64_t acc[NOUT][4];
+  float accb[NOUT];
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
     accb[o] = 0.0f;
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      w[o][c] = Wt[o * K + lane * CPL + c];
-      acc[o][c] = 0.0f;
+    for (int c = 0; c < 4; ++c) acc[o][c] = 0ull;
+    if (HAS_DH) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[o][c] = Wt[o * K + cl * 8 + c];
     }
   }
-  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;
-  const int64_t gstride = (int64_t)gridDim.x * nwarps;
+  const int64_t gw = ((int64_t)blockIdx.x * nwarps + warp) * PPW + sub;
+  const int64_t gstride = (int64_t)gridDim.x * nwarps * PPW;
 #pragma unroll 4
   for (int64_t p = gw; p < P; p += gstride) {
-    bf16 hv[CPL];
-    if constexpr (CPL == 8) *reinterpret_cast<uint4*>(hv) = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + lane * CPL));
-    else if constexpr (CPL == 4) *reinterpret_cast<uint2*>(hv) = __ldg(reinterpret_cast<const uint2*>(h + p * ldh + lane * CPL));
-    else *reinterpret_cast<uint32_t*>(hv) = __ldg(reinterpret_cast<const uint32_t*>(h + p * ldh + lane * CPL));
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + cl * 8));
     float d[NOUT];
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) d[o] = __ldg(d_out + p * ldo + col0 + o);
-    float dh[CPL];
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    uint32_t ov[4];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      float x = __bfloat162float(hv[c]);
-      float t = 0.0f;
+    for (int c = 0; c < 4; ++c) {
+      const float x0 = __uint_as_float(hw[c] << 16), x1 = __uint_as_float(hw[c] & 0xffff0000u);
+      uint64_t xx;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(xx) : "f"(x0), "f"(x1));
 #pragma unroll
       for (int o = 0; o < NOUT; ++o) {
-        acc[o][c] += d[o] * x;
-        t += d[o] * w[o][c];
+        uint64_t dd;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d[o]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o][c]) : "l"(dd), "l"(xx));
       }
-      dh[c] = x > 0.0f ? t : 0.0f;
+      if (HAS_DH) {
+        float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          t0 += d[o] * w[o][2 * c];
+          t1 += d[o] * w[o][2 * c + 1];
+        }
+        const __nv_bfloat162 r = __floats2bfloat162_rn(x0 > 0.0f ? t0 : 0.0f, x1 > 0.0f ? t1 : 0.0f);
+        ov[c] = *reinterpret_cast<const uint32_t*>(&r);
+      }
     }
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) accb[o] += d[o];
-    if (d_h != nullptr) {
-      bf16 ov[CPL];
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) ov[c] = __float2bfloat16_rn(dh[c]);
-      if constexpr (CPL == 8) *reinterpret_cast<uint4*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint4*>(ov);
-      else if constexpr (CPL == 4) *reinterpret_cast<uint2*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint2*>(ov);
-      else *reinterpret_cast<uint32_t*>(d_h + p * ldd + lane * CPL) = *reinterpret_cast<uint32_t*>(ov);
-    }
+    if (HAS_DH) *reinterpret_cast<uint4*>(d_h + p * ldd + cl * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
   }
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) {
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) atomicAdd(&s_acc[o * K + lane * CPL + c], acc[o][c]);
-    if (lane == 0) atomicAdd(&s_acc[NOUT * K + o], accb[o]);
+    for (int c = 0; c < 4; ++c) {
+      float a0, a1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc[o][c]));
+      atomicAdd(&s_acc[o * K + cl * 8 + 2 * c], a0);
+      atomicAdd(&s_acc[o * K + cl * 8 + 2 * c + 1], a1);
+    }
+    if (cl == 0) atomicAdd(&s_acc[NOUT * K + o], accb[o]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) atomicAdd(dW + i, s_acc[i]);
@@ -365,11 +377,15 @@ fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__
     const int o = blockIdx.x;
     for (int k = t; k < W; k += blockDim.x) sh[k] = G[(size_t)o * W + k];
     __syncthreads();
-    for (int j = t; j < W; j += blockDim.x) {
+    // a warp per output column j: lanes stride the contraction index, so the Wf row is read coalesced
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int j = warp; j < W; j += nw) {
       float acc = 0.0f;
       const float* w = Wf + (size_t)j * W;
-      for (int k = 0; k < W; ++k) acc += sh[k] * __bfloat162float(__float2bfloat16_rn(w[k]));
-      dWd[(size_t)o * ldwd + j] += acc + db_dir[o] * bf[j];
+      for (int k = lane; k < W; k += 32) acc += sh[k] * __bfloat162float(__float2bfloat16_rn(w[k]));
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+      if (lane == 0) dWd[(size_t)o * ldwd + j] += acc + db_dir[o] * bf[j];
     }
   } else {  // one feature-layer output row j: dW_feat[j, 0:W], db_feat[j]
     const int j = blockIdx.x - Wh;
@@ -388,13 +404,14 @@ fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__
   }
 }
 
-template <int CPL>
+template <int K>
 int launch_head_bwd_nout(int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
                          int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
-  const int blocks = kNumSMs * 4;  // streaming kernel: exactly the resident blocks (64 regs x 256 threads -> 4 per SM)
-#define NMX_HB(NO)                                                                                               \
-  case NO:                                                                                                       \
-    head_bwd_kernel<CPL, NO><<<blocks, 256, 0, s>>>(h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd);          \
+  const int blocks = kNumSMs * 4;  // streaming kernel: exactly the resident blocks
+#define NMX_HB2(NO, DH) head_bwd_kernel<K, NO, DH><<<blocks, 256, 0, s>>>(h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd)
+#define NMX_HB(NO)                                                         \
+  case NO:                                                                 \
+    if (d_h != nullptr) NMX_HB2(NO, true); else NMX_HB2(NO, false);        \
     break;
   switch (n_out) {
     NMX_HB(1) NMX_HB(2) NMX_HB(3) NMX_HB(4) NMX_HB(5) NMX_HB(6) NMX_HB(7) NMX_HB(8)
@@ -403,15 +420,17 @@ int launch_head_bwd_nout(int n_out, const bf16* h, int ldh, const float* Wt, con
       return NMX_E_BADARG;
   }
 #undef NMX_HB
+#undef NMX_HB2
   NMX_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_head_bwd(int K, int n_out, const bf16* h, int ldh, const float* Wt, const float* d_out, int ldo, int col0,
                     int64_t P, float* dW, float* db, bf16* d_h, int ldd, cudaStream_t s) {
-  if (K == 256) return launch_head_bwd_nout<8>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
-  if (K == 128) return launch_head_bwd_nout<4>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
-  if (K == 64) return launch_head_bwd_nout<2>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  if ((ldh & 7) || (d_h != nullptr && (ldd & 7))) { set_error("head_bwd: leading dimensions must be multiples of 8"); return NMX_E_BADARG; }
+  if (K == 256) return launch_head_bwd_nout<256>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  if (K == 128) return launch_head_bwd_nout<128>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
+  if (K == 64) return launch_head_bwd_nout<64>(n_out, h, ldh, Wt, d_out, ldo, col0, P, dW, db, d_h, ldd, s);
   set_error("head_bwd: K must be 64, 128 or 256 (got %d)", K);
   return NMX_E_UNSUPPORTED;
 }

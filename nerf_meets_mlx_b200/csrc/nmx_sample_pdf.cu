@@ -3,8 +3,12 @@
 //
 // One warp per ray.  The ray's CDF (n+1 edges), padded bin mid-points (n+1) and the N importance samples live in
 // shared memory; every lane owns N/32 samples and runs a branch-free binary search over the shared CDF
-// (searchsorted side="right" == number of edges <= u).  The merge ranks every value by counting
-// (rank = #smaller + #equal-with-lower-concat-index), i.e. exactly a stable sort of concat([z, z_imp]).
+// (searchsorted side="right" == number of edges <= u).  The merge is a stable sort of concat([z, z_imp]): the
+// importance samples are sorted in registers by a warp-wide bitonic network (shuffles for partner distances < 32,
+// compile-time register exchanges above), then both sorted runs find their output slots by binary search in the
+// other run (ties: coarse entries first, as in the concatenation) and the merged row leaves through shared memory
+// as coalesced stores.  Rows whose coarse depths are not ascending, and N > 256, take the O((n+N)^2) rank-counting
+// path (any input gives sort(concat) exactly).
 //
 // CDF arithmetic: w = weights + 0.01 ; sum and running prefix in fp64 rounded to fp32
 // (what torch-CPU cumsum does; both are exact in fp64 for <= 2^20 fp32 addends of this dynamic range, so the
@@ -18,6 +22,46 @@ namespace {
 
 constexpr int kWarps = 4;
 
+// floats of shared memory per warp: cdf[n+1] mid[n+1] z[n] imp[N] out[n+N], every section start a multiple of 4 floats
+// is NOT needed except for `out` (float4 stores) -- the total before it is padded to a multiple of 4
+__host__ __device__ inline int smem_floats_per_warp(int n, int N) {
+  const int head = 2 * (n + 1) + n + N;
+  return ((head + 3) & ~3) + ((n + N + 3) & ~3);
+}
+
+// Ascending bitonic sort of 32*R values held as v[r] = element r*32 + lane.
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(float (&v)[R], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {  // partner lives in another register of the same lane
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & jr) == 0) {
+            const bool asc = (((r * 32) & k) == 0);  // k >= 64 here: decided by the register index alone
+            const float a = v[r], b = v[r | jr];
+            const float lo = fminf(a, b), hi = fmaxf(a, b);
+            v[r] = asc ? lo : hi;
+            v[r | jr] = asc ? hi : lo;
+          }
+        }
+      } else {
+        const bool lower = (lane & j) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const bool asc = (k >= 32) ? (((r * 32) & k) == 0) : ((lane & k) == 0);
+          const float p = __shfl_xor_sync(0xffffffffu, v[r], j);
+          v[r] = (lower == asc) ? fminf(v[r], p) : fmaxf(v[r], p);
+        }
+      }
+    }
+  }
+}
+
+template <int R>
 __global__ void __launch_bounds__(kWarps * 32)
 sample_pdf_kernel(const float* __restrict__ z, const float* __restrict__ weights, const float* __restrict__ u,
                   const float* __restrict__ cdf_in, float eps, float* __restrict__ z_imp, int32_t* __restrict__ inds,
@@ -25,11 +69,12 @@ sample_pdf_kernel(const float* __restrict__ z, const float* __restrict__ weights
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int per_warp = 2 * (n + 1) + n + N;
+  const int per_warp = smem_floats_per_warp(n, N);
   float* s_cdf = smem + (size_t)wib * per_warp;  // [n+1]
   float* s_mid = s_cdf + (n + 1);                // [n+1] padded mid-points
   float* s_z = s_mid + (n + 1);                  // [n] coarse depths
-  float* s_imp = s_z + n;                        // [N] importance samples (unsorted)
+  float* s_imp = s_z + n;                        // [N] importance samples (unsorted, then sorted)
+  float* s_out = s_cdf + ((2 * (n + 1) + n + N + 3) & ~3);  // [n+N] merged row (16 B aligned), staged for coalesced stores
   const int64_t warp0 = (int64_t)blockIdx.x * kWarps + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
   const int n1 = n + 1;
@@ -37,8 +82,11 @@ sample_pdf_kernel(const float* __restrict__ z, const float* __restrict__ weights
   for (int64_t b = warp0; b < B; b += nwarps) {
     const float* zr = z + b * n;
     // ---- coarse depths + padded mid-points (:149-159): mid[0]=mid[1]=m_0 ... mid[n]=m_{n-2}
+    bool z_sorted = true;
     for (int i = lane; i < n; i += 32) s_z[i] = zr[i];
     __syncwarp();
+    for (int i = lane; i < n - 1; i += 32) z_sorted = z_sorted && (s_z[i] <= s_z[i + 1]);
+    z_sorted = __all_sync(0xffffffffu, z_sorted);
     for (int i = lane; i < n1; i += 32) {
       int j = min(max(i - 1, 0), n - 2);
       s_mid[i] = __fdiv_rn(__fadd_rn(s_z[j + 1], s_z[j]), 2.0f);
@@ -98,22 +146,65 @@ sample_pdf_kernel(const float* __restrict__ z, const float* __restrict__ weights
     }
     __syncwarp();
 
-    // ---- stable sort of concat([z (n), imp (N)]) by rank counting
+    // ---- stable sort of concat([z (n), imp (N)])
     if (z_merged != nullptr) {
-      float* outr = z_merged + b * (int64_t)(n + N);
-      for (int i = lane; i < n + N; i += 32) {
-        float v = (i < n) ? s_z[i] : s_imp[i - n];
-        int rank = 0;
-        // concat index order: all coarse entries precede all importance entries
-        for (int k = 0; k < n; ++k) {
-          float o = s_z[k];
-          rank += (o < v) || (o == v && k < i);
+      const int tot = n + N;
+      if (R > 0 && z_sorted) {
+        float v[R > 0 ? R : 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = (r * 32 + lane < N) ? s_imp[r * 32 + lane] : __int_as_float(0x7f800000);
+        __syncwarp();
+        warp_bitonic_sort<(R > 0 ? R : 1)>(v, lane);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r * 32 + lane < N) s_imp[r * 32 + lane] = v[r];
+        __syncwarp();
+        // importance sample e lands at e + #(coarse <= v): coarse entries come first among equals
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          if (e < N) {
+            int lo = 0, hi = n;
+            while (lo < hi) {
+              const int mid = (lo + hi) >> 1;
+              if (s_z[mid] <= v[r]) lo = mid + 1; else hi = mid;
+            }
+            s_out[e + lo] = v[r];
+          }
         }
-        for (int k = 0; k < N; ++k) {
-          float o = s_imp[k];
-          rank += (o < v) || (o == v && (k + n) < i);
+        // coarse entry i lands at i + #(importance < z_i)
+        for (int i = lane; i < n; i += 32) {
+          const float zv = s_z[i];
+          int lo = 0, hi = N;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_imp[mid] < zv) lo = mid + 1; else hi = mid;
+          }
+          s_out[i + lo] = zv;
         }
-        outr[rank] = v;
+      } else {
+        // rank counting (rank = #smaller + #equal-with-lower-concat-index): any input order
+        for (int i = lane; i < tot; i += 32) {
+          float v = (i < n) ? s_z[i] : s_imp[i - n];
+          int rank = 0;
+          for (int k = 0; k < n; ++k) {
+            float o = s_z[k];
+            rank += (o < v) || (o == v && k < i);
+          }
+          for (int k = 0; k < N; ++k) {
+            float o = s_imp[k];
+            rank += (o < v) || (o == v && (k + n) < i);
+          }
+          s_out[rank] = v;
+        }
+      }
+      __syncwarp();
+      float* outr = z_merged + b * (int64_t)tot;
+      if ((tot & 3) == 0) {
+        for (int i = lane * 4; i < tot; i += 128)
+          *reinterpret_cast<float4*>(outr + i) = *reinterpret_cast<const float4*>(s_out + i);
+      } else {
+        for (int i = lane; i < tot; i += 32) outr[i] = s_out[i];
       }
     }
     __syncwarp();
@@ -154,15 +245,21 @@ extern "C" int nmx_sample_pdf_fwd(const float* z, const float* weights, const fl
   NMX_CHECK_ARG(B >= 0 && n >= 2 && N >= 1, "B >= 0, n >= 2, N >= 1");
   if (B == 0) return 0;
   NMX_CHECK_ARG(z && u && (weights || cdf_in), "z, u and one of weights / cdf_in must be non-null");
-  size_t smem = (size_t)kWarps * (2 * (n + 1) + n + N) * sizeof(float);
+  size_t smem = (size_t)kWarps * smem_floats_per_warp(n, N) * sizeof(float);
   NMX_CHECK_ARG(smem <= 200 * 1024, "n + N too large for shared memory");
-  if (smem > 48 * 1024)
-    NMX_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = grid_for(B, kWarps, 16);
-  sample_pdf_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, weights, u, cdf_in, eps, z_imp, inds,
-                                                                         cdf_out, z_merged, B, n, N);
-  NMX_LAUNCH_CHECK();
-  return 0;
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024) NMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, weights, u, cdf_in, eps, z_imp, inds, cdf_out, z_merged, B, n, N);
+    NMX_LAUNCH_CHECK();
+    return 0;
+  };
+  // registers per lane for the bitonic network: 32*R >= N (R = 0: rank-counting path only)
+  if (N <= 32) return go(sample_pdf_kernel<1>);
+  if (N <= 64) return go(sample_pdf_kernel<2>);
+  if (N <= 128) return go(sample_pdf_kernel<4>);
+  if (N <= 256) return go(sample_pdf_kernel<8>);
+  return go(sample_pdf_kernel<0>);
 }
 
 extern "C" int nmx_sort_merge_z(const float* a, const float* b, float* out, int64_t B, int na, int nb, void* stream) {

@@ -173,7 +173,8 @@ def test_sample_pdf_indices_bit_exact_given_reference_cdf(ops, golden):
         np.testing.assert_array_equal(r["z_merged"].cpu().numpy(), ref_sorted)
 
 
-@pytest.mark.parametrize("B,n,N", [(1, 64, 128), (513, 64, 128), (33, 16, 40), (7, 192, 64), (3, 2, 5)])
+@pytest.mark.parametrize("B,n,N", [(1, 64, 128), (513, 64, 128), (33, 16, 40), (7, 192, 64), (3, 2, 5), (19, 64, 256),
+                                   (5, 64, 300), (9, 33, 97), (40000, 64, 128)])
 def test_sample_pdf_vs_oracle_bit_exact(ops, B, n, N):
     rng = np.random.default_rng(B + n)
     z = np.sort(rng.uniform(2, 6, size=(B, n)).astype(np.float32), -1)
@@ -195,6 +196,23 @@ def test_sample_pdf_vs_oracle_bit_exact(ops, B, n, N):
     np.testing.assert_array_equal(r["z_merged"].cpu().numpy(), osamp.merge_sorted(z, out))
     m = r["z_merged"].cpu().numpy()
     assert np.all(np.diff(m, axis=-1) >= 0)
+
+
+def test_sample_pdf_merge_unsorted_coarse_depths_and_ties(ops):
+    """sort(concat) must hold for ANY coarse row (rank-counting path) and with heavy ties (degenerate CDF bins collapse
+    many samples onto the same mid-point; coarse duplicates)."""
+    rng = np.random.default_rng(77)
+    B, n, N = 65, 64, 128
+    z = rng.uniform(2, 6, size=(B, n)).astype(np.float32)           # not sorted
+    z[1::2] = np.sort(z[1::2], -1)                                   # every other row sorted: both paths in one launch
+    z[3, 10:20] = z[3, 10]                                           # duplicated coarse depths
+    w = np.zeros((B, n, 1), np.float32)
+    w[:, 5] = 1.0                                                    # one-hot weights: most samples share a bin
+    u = rng.random(size=(B, N), dtype=np.float32)
+    u[:, ::3] = u[:, :1]                                             # repeated draws -> exactly equal samples
+    r = ops.sample_pdf(dev(z), dev(w), dev(u))
+    imp = r["z_imp"].cpu().numpy()
+    np.testing.assert_array_equal(r["z_merged"].cpu().numpy(), np.sort(np.concatenate([z, imp], -1), -1))
 
 
 def test_sort_merge(ops):

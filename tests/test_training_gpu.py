@@ -186,4 +186,7 @@ def test_train_iteration_from_pixels_matches_ray_inputs():
             rd = torch.from_numpy(np.reshape(rd, (-1, 3))[pix].astype(np.float32)).cuda()
             r = tr.train_iteration(ro, rd, torch.from_numpy(img[pix]).cuda(), u_vals=u)
         losses.append((float(r["loss_coarse"]), float(r["loss_fine"])))
-    assert losses[0] == losses[1]
+    # same rays and targets: the coarse loss is a deterministic forward; the fine loss sees the coarse net after an
+    # update whose weight gradients were reduced with fp32 atomics (order-dependent in the last bits)
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[1][0])
+    assert abs(losses[0][1] - losses[1][1]) <= 1e-3 * abs(losses[1][1])
