@@ -20,6 +20,10 @@
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
 #include "nmx_chain.cuh"
+
+#ifndef NMX_EPI_QUARTER
+#define NMX_EPI_QUARTER 1  // forward epilogue granularity: 1 = one 64-column chunk per step (16 warps x 16 columns)
+#endif
 #include "nmx_gemm.cuh"
 
 using namespace nmx;
@@ -153,15 +157,17 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
 // optional register heads.  HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
 // The TMEM load of chunk c+1 is issued before the math of chunk c (two register sets).
 // math + store of 32 columns [c0, c0 + 32) of chunk c held in r[] (fp32 accumulators of this thread's row)
-template <bool RELU, int HEAD>
-__device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
-                                         const uint32_t bias_addr, const uint32_t act_row_addr, const uint32_t swz,
-                                         const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3],
-                                         const uint32_t bits_addr) {
+// NP4 = number of 8-column pieces (4: 32 columns, 2: 16 columns); piece0 = index of the first 16-byte piece inside the
+// chunk's 128-byte row; bit0 = first pair index of these columns inside their 32-column sign-bit word.
+template <bool RELU, int HEAD, int NP4, bool BITS>
+__device__ __forceinline__ void epi_cols(const uint32_t (&r)[8 * NP4], const int c, const int c0, const int piece0,
+                                         const int bit0, const uint32_t bias_addr, const uint32_t act_row_addr,
+                                         const uint32_t swz, const uint32_t hw_addr, const int head_n, float (&hp)[8],
+                                         float (&rgbp)[3], const uint32_t bits_addr) {
   const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
-  uint32_t bits = 0;  // ReLU sign bits of this thread's 32 columns (bit e / 16+e = columns 2e / 2e+1)
+  uint32_t bits = 0;  // ReLU sign bits of this thread's columns (bit e / 16+e = columns 2e / 2e+1 of the 32-column word)
 #pragma unroll
-  for (int p4 = 0; p4 < 4; ++p4) {
+  for (int p4 = 0; p4 < NP4; ++p4) {
     const float4 b0 = lds128(bias_addr + (uint32_t)(c0 + p4 * 8) * 4u);
     const float4 b1 = lds128(bias_addr + (uint32_t)(c0 + p4 * 8 + 4) * 4u);
     const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -171,9 +177,9 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, c
       const uint64_t x = add_f32x2(pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]),
                                    pack64(__float_as_uint(bv[2 * e]), __float_as_uint(bv[2 * e + 1])));
       pk[e] = cvt_bf16x2<RELU>(x);
-      if (RELU) bits |= nz_mask_bf16x2(pk[e]) & (0x00010001u << (p4 * 4 + e));
+      if (RELU && BITS) bits |= nz_mask_bf16x2(pk[e]) & (0x00010001u << (bit0 + p4 * 4 + e));
     }
-    sts128(so + ((((uint32_t)(sub * 4 + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+    sts128(so + ((((uint32_t)(piece0 + p4)) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
     if (HEAD != 0) {
       float xr[8];  // the bf16-rounded activations (what a separate head kernel would read back)
 #pragma unroll
@@ -203,21 +209,56 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[32], const int c, c
       }
     }
   }
-  if (RELU && bits_addr != 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(bits_addr), "r"(bits) : "memory");
-  fence_proxy_async_smem();
+  if (RELU && BITS && bits_addr != 0) {
+    if (NP4 == 4) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(bits_addr), "r"(bits) : "memory");
+    } else {  // half a word: pairs bit0..bit0+7 live in byte bit0/8 (even columns) and byte 2 + bit0/8 (odd columns)
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(bits_addr + (uint32_t)(bit0 >> 3)), "r"((bits >> bit0) & 0xffu) : "memory");
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(bits_addr + 2u + (uint32_t)(bit0 >> 3)), "r"((bits >> (16 + bit0)) & 0xffu) : "memory");
+    }
+  }
+  if (NP4 == 4) fence_proxy_async_smem();  // quarter steps: the caller fences after issuing the next TMEM load
 }
 
 // Epilogue of one layer for one warp.  Half-phase h (accumulator columns [128h, 128h+128) = chunks 2h, 2h+1):
 // this warp takes 32 columns of one of the two chunks: TMEM -> (+bias, ReLU) -> bf16 -> swizzled smem chunk (A operand
 // of the next layer / TMA-store source), optional register heads.
 // HEAD: 0 none, 1 alpha (one output), 2 rgb, 3 output_linear (up to 8 outputs).
-template <bool RELU, int HEAD>
+template <bool RELU, int HEAD, bool BITS>
 __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halves, uint64_t* tfull2, const uint32_t aphase,
                                           const int part, const uint32_t bias_addr, const uint32_t act_row_addr,
                                           const uint32_t swz, uint64_t* act_ready, const bool signal, const int lane,
                                           const uint32_t hw_addr, const int head_n, float (&hp)[8], float (&rgbp)[3],
                                           const bool skip_math, const bool tr_on, const int it, const int l,
                                           const uint32_t bits_row_addr) {
+#if NMX_EPI_QUARTER
+  // Quarter steps: all 16 epilogue warps work on ONE 64-column chunk at a time (16 columns per warp), so the first
+  // K-slab of the next layer is released after a quarter of the epilogue instead of half of it.  The TMEM load of
+  // step s+1 is issued as soon as the math of step s has consumed the registers, i.e. it is in flight during the
+  // proxy fence and the barrier arrival of step s.
+  const int nsteps = 2 * n_halves;
+  (void)skip_math;  // debug switch of the half-step variant only
+  uint32_t r[16];
+  mbar_wait(&tfull2[0], aphase);
+  trace(tr_on, 1, it, l, 0);
+  tc_fence_after();
+  tmem_ld_32x16(tacc + (uint32_t)(part * 16), r);
+#pragma unroll 1
+  for (int st = 0; st < nsteps; ++st) {
+    tmem_ld_wait_regs<16>(r);
+    if (st == 0) trace(tr_on, 1, it, l, 1);
+    epi_cols<RELU, HEAD, 2, BITS>(r, st, st * 64 + part * 16, 2 * part, 8 * (part & 1), bias_addr, act_row_addr, swz, hw_addr,
+                            head_n, hp, rgbp, bits_row_addr ? bits_row_addr + (uint32_t)(2 * st + (part >> 1)) * 4u : 0u);
+    if (st == 1) {  // columns 128.. belong to the second commit (same instant for N = 256; keeps the phases in step)
+      mbar_wait(&tfull2[1], aphase);
+      tc_fence_after();
+    }
+    if (st + 1 < nsteps) tmem_ld_32x16(tacc + (uint32_t)((st + 1) * 64 + part * 16), r);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (signal && lane == 0) mbar_arrive(&act_ready[st]);
+  }
+#else
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     mbar_wait(&tfull2[h], aphase);
@@ -232,13 +273,14 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
         tmem_ld_32x32(tacc + (uint32_t)c0, r);
         tmem_ld_wait_regs<32>(r);
         if (h == 0) trace(tr_on, 1, it, l, 1);
-        epi_cols<RELU, HEAD>(r, c, c0, sub, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp,
-                             bits_row_addr ? bits_row_addr + (uint32_t)(4 * h + part) * 4u : 0u);
+        epi_cols<RELU, HEAD, 4, BITS>(r, c, c0, sub * 4, 0, bias_addr, act_row_addr, swz, hw_addr, head_n, hp, rgbp,
+                                bits_row_addr ? bits_row_addr + (uint32_t)(4 * h + part) * 4u : 0u);
       }
       __syncwarp();
       if (signal && lane == 0) mbar_arrive(&act_ready[c]);
     }
   }
+#endif
 }
 
 // backward epilogue of 32 columns: bf16((acc [+ d_sigma * w_alpha]) masked by the ReLU sign bits of the saved
@@ -332,7 +374,9 @@ __device__ __forceinline__ void encode_pos_row(const float* __restrict__ rays, i
 // 201-243): step A computes d_hd = (d_rgb W_rgb) * [hd > 0] on the CUDA cores, then every layer is
 // dX = dY W (W^T copies as the K-major B operand), with the ReLU mask of the saved activation (and the alpha head's
 // rank-1 term d_sigma (x) w_alpha on the feature layer) in the epilogue; every dY is TMA-stored for the wgrad kernels.
-template <int MODE>
+// SAVE (forward): the training variant keeps activations + ReLU sign bits; the inference variant compiles all of that
+// out of the epilogue (the epilogue warps are issue-bound: every instruction per column counts).
+template <int MODE, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) {
   using SL = SmemT<MODE>;
@@ -367,7 +411,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
   const int lane = threadIdx.x & 31;
   const int num_tiles = (prm.P + 127) / 128;
   const int NL = prm.n_layers;
-  const bool save = prm.save != 0;
+  constexpr bool save = SAVE;
 
   if (warp == kTmaWarp && lane == 0) {
     for (int l = 0; l < NL; ++l) tma_prefetch_desc(&maps.w[l]);
@@ -382,7 +426,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     }
     for (int i = 0; i < 4; ++i) mbar_init(&tfull[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&tempty[i], kEpiWarps);
-    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], kEpiWarps / 2);
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], (MODE == 0 && NMX_EPI_QUARTER) ? kEpiWarps : kEpiWarps / 2);
     mbar_init(x0pos_full, 1);
     mbar_init(x0pos_empty, 1);
     mbar_init(x0dir_full, 1);
@@ -735,19 +779,19 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
                                    ? smem_u32(s_bits) + (uint32_t)row_local * 32u : 0u;
           uint64_t* tf = &tfull[as * 2];
           if (l == prm.head7_layer && prm.head7_n == 1)
-            epi_layer<true, 1>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+            epi_layer<true, 1, SAVE>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
                                w7_addr, 1, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (l == prm.head7_layer)
-            epi_layer<true, 3>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+            epi_layer<true, 3, SAVE>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
                                w7_addr, prm.head7_n, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (l == prm.rgb_layer)
-            epi_layer<true, 2>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
+            epi_layer<true, 2, SAVE>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane,
                                wrgb_addr, 0, hp, rgbp, skip_math, tr_on, it, l, bra);
           else if (prm.L[l].relu)
-            epi_layer<true, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+            epi_layer<true, 0, SAVE>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
                                0, hp, rgbp, skip_math, tr_on, it, l, bra);
           else
-            epi_layer<false, 0>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
+            epi_layer<false, 0, false>(tacc, n_halves, tf, aphase, part, bias_addr, act_row_addr, swz, act_ready, signal, lane, 0,
                                 0, hp, rgbp, skip_math, tr_on, it, l, bra);
           trace(tr_on, 1, it, l, 2);
           tc_fence_before();
@@ -955,7 +999,9 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaSt
   }
   static bool attr = false;
   if (!attr) {
-    NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<MODE>::kAlloc));
+    NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<MODE>::kAlloc));
+    if (MODE == 0)
+      NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<0>::kAlloc));
     attr = true;
   }
   int tiles = (prm.P + 127) / 128;
@@ -964,7 +1010,8 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaSt
   double flops = 0.0;  // padded flops actually issued to the tensor pipe
   for (int l = 0; l < prm.n_layers; ++l) flops += 2.0 * prm.P * prm.L[l].N * 64.0 * prm.L[l].n_slabs;
   prof_begin(MODE == 1 ? 4 : (prm.save ? 3 : 2), flops, stream);
-  mlp_chain_kernel<MODE><<<grid, kThreads, SmemT<MODE>::kAlloc, stream>>>(maps, prm);
+  if (MODE == 0 && !prm.save) mlp_chain_kernel<0, false><<<grid, kThreads, SmemT<0>::kAlloc, stream>>>(maps, prm);
+  else mlp_chain_kernel<MODE, true><<<grid, kThreads, SmemT<MODE>::kAlloc, stream>>>(maps, prm);
   prof_end(stream);
   NMX_LAUNCH_CHECK();
   return 0;

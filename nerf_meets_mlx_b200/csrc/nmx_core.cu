@@ -132,27 +132,39 @@ extern "C" int nmx_ray_points_fwd(const float* rays, int ray_stride, const float
 //   else k=(c-inc)/(2*in_dim), r=(c-inc)%(2*in_dim), fn = r/in_dim (0 sin, 1 cos), d = r%in_dim,
 //        f_k = k^2 (reference quirk) ; out = fn(x[d]*f_k)
 // Full-range sinf/cosf (no fast-math): arguments reach |x|*81.
-__global__ void pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t total, int in_dim,
-                                   int n_freqs, int inc) {
-  int out_dim = inc + 2 * in_dim * n_freqs;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = idx / out_dim;
-    int c = (int)(idx - p * out_dim);
-    float v;
-    if (c < inc) {
-      v = x[p * in_dim + c];
-    } else {
-      int q = c - inc;
-      int k = q / (2 * in_dim);
-      int r = q - k * 2 * in_dim;
-      int fn = r / in_dim;
-      int d = r - fn * in_dim;
-      float f = (float)(k * k);
-      float a = __fmul_rn(x[p * in_dim + d], f);
-      v = fn ? cosf(a) : sinf(a);
+// A block encodes tiles of 32 points: threads take (point, frequency, dim) items and produce sin and cos together
+// (sincosf), rows are staged in shared memory and the tile leaves as one contiguous, coalesced span -- several
+// independent range reductions in flight per thread, no 64-bit index division per element.
+constexpr int kPeTile = 32;
+__global__ void __launch_bounds__(256)
+pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t P, int in_dim, int n_freqs, int inc) {
+  extern __shared__ float s_rows[];
+  const int out_dim = inc + 2 * in_dim * n_freqs;
+  const int items = in_dim * n_freqs;
+  float* s_x = s_rows + kPeTile * out_dim;  // [kPeTile * in_dim]
+  for (int64_t p0 = (int64_t)blockIdx.x * kPeTile; p0 < P; p0 += (int64_t)gridDim.x * kPeTile) {
+    const int np = (int)((P - p0 < kPeTile) ? (P - p0) : kPeTile);
+    for (int i = threadIdx.x; i < np * in_dim; i += 256) s_x[i] = x[p0 * in_dim + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * inc; i += 256) {
+      const int pt = i / inc, c = i - pt * inc;
+      s_rows[pt * out_dim + c] = s_x[pt * in_dim + c];
     }
-    out[idx] = v;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < np * items; i += 256) {
+      const int pt = i / items, q = i - pt * items;
+      const int k = q / in_dim, d = q - k * in_dim;
+      const float a = __fmul_rn(s_x[pt * in_dim + d], (float)(k * k));
+      float sv, cv;
+      sincosf(a, &sv, &cv);
+      float* row = s_rows + pt * out_dim + inc + k * 2 * in_dim;
+      row[d] = sv;
+      row[in_dim + d] = cv;
+    }
+    __syncthreads();
+    float* o = out + p0 * out_dim;
+    for (int i = threadIdx.x; i < np * out_dim; i += 256) o[i] = s_rows[i];
+    __syncthreads();
   }
 }
 
@@ -161,9 +173,12 @@ extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in
   NMX_CHECK_ARG(P >= 0 && in_dim >= 1 && n_freqs >= 0, "P >= 0, in_dim >= 1, n_freqs >= 0");
   if (P == 0) return 0;
   int inc = include_input ? in_dim : 0;
-  int64_t total = P * (inc + 2 * in_dim * n_freqs);
-  if (total == 0) return 0;
-  pe_embedder_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, out, total, in_dim, n_freqs, inc);
+  const int out_dim = inc + 2 * in_dim * n_freqs;
+  if (out_dim == 0) return 0;
+  NMX_CHECK_ARG(out_dim <= 1024, "encoded width <= 1024");
+  const size_t smem = (size_t)kPeTile * (out_dim + in_dim) * sizeof(float);
+  if (smem > 48 * 1024) NMX_CUDA(cudaFuncSetAttribute(pe_embedder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pe_embedder_kernel<<<grid_for(P, kPeTile, 16), 256, smem, (cudaStream_t)stream>>>(x, out, P, in_dim, n_freqs, inc);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -172,26 +187,27 @@ extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in
 //   c < in_dim*n_freqs      -> sin(x[d]*band[k]),            d = c / n_freqs, k = c % n_freqs
 //   c < 2*in_dim*n_freqs    -> sin(x[d]*band[k] + fp32(pi/2))  (the reference's cos)
 //   else                    -> x[c - 2*in_dim*n_freqs]
-__global__ void pe_sinusoidal_kernel(const float* __restrict__ x, const float* __restrict__ bands,
-                                     float* __restrict__ out, int64_t total, int in_dim, int n_freqs, int out_dim) {
+__global__ void __launch_bounds__(256)
+pe_sinusoidal_kernel(const float* __restrict__ x, const float* __restrict__ bands, float* __restrict__ out, int64_t P,
+                     int in_dim, int n_freqs, int out_dim) {
+  extern __shared__ float s_rows[];
   const float half_pi = 1.57079637050628662109375f;  // fp32(pi/2)
-  int half = in_dim * n_freqs;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = idx / out_dim;
-    int c = (int)(idx - p * out_dim);
-    float v;
-    if (c < 2 * half) {
-      int q = (c < half) ? c : c - half;
-      int d = q / n_freqs;
-      int k = q - d * n_freqs;
-      float s = __fmul_rn(x[p * in_dim + d], bands[k]);
-      if (c >= half) s = __fadd_rn(s, half_pi);
-      v = sinf(s);
-    } else {
-      v = x[p * in_dim + (c - 2 * half)];
+  const int half = in_dim * n_freqs;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* row = s_rows + warp * out_dim;
+  for (int64_t p = (int64_t)blockIdx.x * nw + warp; p < P; p += (int64_t)gridDim.x * nw) {
+    const float* xp = x + p * in_dim;
+    for (int q = lane; q < half; q += 32) {
+      const int d = q / n_freqs, k = q - d * n_freqs;
+      const float sc = __fmul_rn(xp[d], bands[k]);
+      row[q] = sinf(sc);
+      row[half + q] = sinf(__fadd_rn(sc, half_pi));
     }
-    out[idx] = v;
+    for (int c = 2 * half + lane; c < out_dim; c += 32) row[c] = xp[c - 2 * half];
+    __syncwarp();
+    float* o = out + p * out_dim;
+    for (int c = lane; c < out_dim; c += 32) o[c] = row[c];
+    __syncwarp();
   }
 }
 
@@ -200,8 +216,8 @@ extern "C" int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* 
   NMX_CHECK_ARG(P >= 0 && in_dim >= 1 && n_freqs >= 1, "P >= 0, in_dim >= 1, n_freqs >= 1");
   if (P == 0) return 0;
   int out_dim = 2 * in_dim * n_freqs + (include_input ? in_dim : 0);
-  int64_t total = P * out_dim;
-  pe_sinusoidal_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, bands, out, total, in_dim, n_freqs, out_dim);
+  NMX_CHECK_ARG(out_dim <= 1024, "encoded width <= 1024");
+  pe_sinusoidal_kernel<<<grid_for(P, 8, 16), 256, 8 * out_dim * sizeof(float), (cudaStream_t)stream>>>(x, bands, out, P, in_dim, n_freqs, out_dim);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -210,16 +226,21 @@ extern "C" int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* 
 // Spherical-harmonics direction encoding, degree <= 4 (encoding/spherical_harmonics.py:33-94).  One thread per
 // direction; every product / sum is a separately rounded fp32 operation in the reference's evaluation order
 // (Python scalar * fp32 array stays fp32), so the result is bit-comparable with the restated reference.
-__global__ void sh_encode_kernel(const float* __restrict__ dirs, int in_dim, float* __restrict__ out, int64_t B,
-                                 int level) {
+__global__ void __launch_bounds__(256)
+sh_encode_kernel(const float* __restrict__ dirs, int in_dim, float* __restrict__ out, int64_t B, int level) {
+  // one thread per direction; the block's 256 rows are staged in shared memory (row pitch od: odd for every level, so
+  // the strided per-thread writes are conflict-free) and written out as one contiguous, coalesced span
+  extern __shared__ float s_tile[];
   const int od = (level + 1) * (level + 1);
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < B; p += (int64_t)gridDim.x * blockDim.x) {
-    const float x = dirs[p * in_dim + 0], y = dirs[p * in_dim + 1], z = dirs[p * in_dim + 2];
+  for (int64_t p0 = (int64_t)blockIdx.x * 256; p0 < B; p0 += (int64_t)gridDim.x * 256) {
+    const int64_t p = p0 + threadIdx.x;
+    const int64_t pc = p < B ? p : B - 1;
+    const float x = dirs[pc * in_dim + 0], y = dirs[pc * in_dim + 1], z = dirs[pc * in_dim + 2];
 #define M_(a, b) __fmul_rn((a), (b))
 #define S_(a, b) __fsub_rn((a), (b))
 #define A_(a, b) __fadd_rn((a), (b))
     const float xx = M_(x, x), yy = M_(y, y), zz = M_(z, z), xy = M_(x, y), yz = M_(y, z), xz = M_(x, z);
-    float* o = out + p * od;
+    float* o = s_tile + threadIdx.x * od;
     o[0] = 0.28209479177387814f;
     if (level >= 1) {
       o[1] = M_(0.4886025119029199f, y);
@@ -257,6 +278,12 @@ __global__ void sh_encode_kernel(const float* __restrict__ dirs, int in_dim, flo
 #undef M_
 #undef S_
 #undef A_
+    __syncthreads();
+    const int64_t nrow = (B - p0 < 256) ? (B - p0) : 256;
+    const int n_out = (int)nrow * od;
+    float* dst = out + p0 * od;
+    for (int i = threadIdx.x; i < n_out; i += 256) dst[i] = s_tile[i];
+    __syncthreads();
   }
 }
 
@@ -264,7 +291,8 @@ extern "C" int nmx_sh_encode_fwd(const float* dirs, int in_dim, float* out, int6
   NMX_CHECK_ARG(B >= 0 && in_dim >= 3 && n_degrees >= 0 && n_degrees <= 4, "B >= 0, in_dim >= 3, 0 <= n_degrees <= 4");
   if (B == 0) return 0;
   NMX_CHECK_ARG(dirs && out, "dirs, out non-null");
-  sh_encode_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(dirs, in_dim, out, B, n_degrees);
+  const int od = (n_degrees + 1) * (n_degrees + 1);
+  sh_encode_kernel<<<grid_for(B, 256, 16), 256, 256 * od * sizeof(float), (cudaStream_t)stream>>>(dirs, in_dim, out, B, n_degrees);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -274,12 +302,16 @@ extern "C" int nmx_sh_encode_fwd(const float* dirs, int in_dim, float* out, int6
 // __test_nerf.py:208-236): pixel id -> [o(3), d(3), near, far, viewdirs(3)] and, optionally, the target pixel.
 // get_rays runs in float64 in the reference when K is a float64 array (NumPy >= 2 promotion) and is cast to fp32
 // afterwards: the same here, with separately rounded products and the sequential 3-term sum NumPy uses.
-__global__ void gen_rays_kernel(const float* __restrict__ c2w, int c2w_ld, double fx, double fy, double cx, double cy,
+__global__ void __launch_bounds__(256) gen_rays_kernel(const float* __restrict__ c2w, int c2w_ld, double fx, double fy, double cx, double cy,
                                 int W, const int32_t* __restrict__ pix, int64_t B, float near, float far,
                                 float* __restrict__ rays, int ray_stride, const float* __restrict__ image, int img_ld,
                                 float* __restrict__ target) {
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t id = pix ? (int64_t)pix[b] : b;
+  // one thread per ray; rows are staged in shared memory (pitch 6 / 8 / 11 floats) and stored as one coalesced span
+  extern __shared__ float s_tile[];
+  for (int64_t b0 = (int64_t)blockIdx.x * 256; b0 < B; b0 += (int64_t)gridDim.x * 256) {
+    const int64_t b = b0 + threadIdx.x;
+    const bool live = b < B;
+    const int64_t id = live ? (pix ? (int64_t)pix[b] : b) : 0;
     const int row = (int)(id / W), col = (int)(id - (int64_t)row * W);
     const double d0 = __ddiv_rn(__dsub_rn((double)(float)col, cx), fx);
     const double d1 = -__ddiv_rn(__dsub_rn((double)(float)row, cy), fy);
@@ -291,7 +323,7 @@ __global__ void gen_rays_kernel(const float* __restrict__ c2w, int c2w_ld, doubl
                                  __dmul_rn(d2, (double)c2w[r * c2w_ld + 2]));
       d[r] = (float)v;
     }
-    float* o = rays + b * ray_stride;
+    float* o = s_tile + threadIdx.x * ray_stride;
     o[0] = c2w[0 * c2w_ld + 3];
     o[1] = c2w[1 * c2w_ld + 3];
     o[2] = c2w[2 * c2w_ld + 3];
@@ -302,10 +334,20 @@ __global__ void gen_rays_kernel(const float* __restrict__ c2w, int c2w_ld, doubl
       const float nrm = __fsqrt_rn(n2);
       o[8] = __fdiv_rn(d[0], nrm); o[9] = __fdiv_rn(d[1], nrm); o[10] = __fdiv_rn(d[2], nrm);
     }
-    if (target) {
+    float* t = s_tile + 256 * ray_stride + threadIdx.x * 3;
+    if (target && live) {
       const float* px = image + id * img_ld;
-      target[b * 3 + 0] = px[0]; target[b * 3 + 1] = px[1]; target[b * 3 + 2] = px[2];
+      t[0] = px[0]; t[1] = px[1]; t[2] = px[2];
     }
+    __syncthreads();
+    const int nrow = (int)((B - b0 < 256) ? (B - b0) : 256);
+    float* dst = rays + b0 * ray_stride;
+    for (int i = threadIdx.x; i < nrow * ray_stride; i += 256) dst[i] = s_tile[i];
+    if (target) {
+      float* td = target + b0 * 3;
+      for (int i = threadIdx.x; i < nrow * 3; i += 256) td[i] = s_tile[256 * ray_stride + i];
+    }
+    __syncthreads();
   }
 }
 
@@ -319,7 +361,7 @@ extern "C" int nmx_gen_rays(const float* c2w, int c2w_ld, double fx, double fy, 
   NMX_CHECK_ARG(pix != nullptr || B <= (int64_t)H * W, "without pixel ids B <= H*W");
   if (B == 0) return 0;
   NMX_CHECK_ARG(c2w && rays, "c2w, rays non-null");
-  gen_rays_kernel<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(c2w, c2w_ld, fx, fy, cx, cy, W, pix, B, near, far,
+  gen_rays_kernel<<<grid_for(B, 256, 16), 256, 256 * (ray_stride + 3) * sizeof(float), (cudaStream_t)stream>>>(c2w, c2w_ld, fx, fy, cx, cy, W, pix, B, near, far,
                                                                       rays, ray_stride, image, img_ld, target);
   NMX_LAUNCH_CHECK();
   return 0;
