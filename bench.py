@@ -287,9 +287,18 @@ def run_ours(args):
                 sub[name] = {"tflops": alg[k] * prof_steps / (prof[k][0] * 1e-3) / 1e12, "launches": int(prof[k][2]),
                              "ms_per_step": prof[k][0] / prof_steps}
         # wgrad: HBM-bound (reads dY[P,M] and X[P,N] bf16 once per launch)
-        wg_shapes = [(256, 64)] + [(256, 256)] * 7 + [(256, 64)] + [(256, 256)] + [(128, 256), (128, 64)]
-        wg_bytes = sum(2 * (m + n) for m, n in wg_shapes) * (P_c + P_f) * prof_steps
+        # bf16 bytes per point: layer 0 (dY 512 + PE(pos) 128), six plain layers (512 + 512), the skip layer as ONE
+        # dual-operand launch (dY 512 + h 512 + PE(pos) 128), the dir layer as one dual launch (d_hd 256 + h 512 +
+        # PE(dir) 128).  Part of it is served by L2 (dY was written by the chain just before), so the figure can exceed
+        # the HBM peak.
+        wg_bytes_per_point = 640 + 7 * 1024 + 1152 + 896
+        wg_bytes = wg_bytes_per_point * (P_c + P_f) * prof_steps
         wg_ms = prof[1][0]
+        chain_traffic = {}
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_v9_chain_traffic.json")
+        if world == 1 and os.path.exists(tpath):  # ncu --set full capture of the same six launches per step (N = 1 sizes)
+            with open(tpath) as f:
+                chain_traffic = json.load(f)
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -312,7 +321,8 @@ def run_ours(args):
                          "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops_sustained"],
                          "peak_source": peak_src + " sustained (timed inside a long step)",
-                         "launches": int(chain_n), "avg_launch_ms": chain_ms / max(chain_n, 1), "traffic": None,
+                         "launches": int(chain_n), "avg_launch_ms": chain_ms / max(chain_n, 1),
+                         "traffic": chain_traffic.get("dram_bytes_per_launch"), "traffic_source": chain_traffic.get("source"),
                          "modes": sub, "profiled_steps": prof_steps,
                          "wgrad": {"bound": "hbm", "achieved": wg_bytes / (wg_ms * 1e-3) / 1e9 if wg_ms > 0 else 0.0,
                                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
