@@ -285,15 +285,16 @@ __device__ __forceinline__ void epi_layer(const uint32_t tacc, const int n_halve
 
 // backward epilogue of 32 columns: bf16((acc [+ d_sigma * w_alpha]) masked by the ReLU sign bits of the saved
 // activation (`bits`: bit e / 16+e = columns 2e / 2e+1 of this thread's 32 columns)).
-template <int EPI>
-__device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, const int c0, const int sub,
-                                         const uint32_t act_row_addr, const uint32_t swz, const uint32_t bits,
-                                         const uint32_t wa_addr, const float ds) {
+// NP4 / piece0 / bit0 as in epi_cols (4: 32 columns = a whole sign-bit word; 2: 16 columns = pairs bit0..bit0+7 of it).
+template <int EPI, int NP4>
+__device__ __forceinline__ void bwd_cols(const uint32_t (&r)[8 * NP4], const int c, const int c0, const int piece0,
+                                         const int bit0, const uint32_t act_row_addr, const uint32_t swz,
+                                         const uint32_t bits, const uint32_t wa_addr, const float ds) {
   const uint32_t so = act_row_addr + (uint32_t)c * kChunkBytes;
   const uint64_t ds2 = pack64(__float_as_uint(ds), __float_as_uint(ds));
 #pragma unroll
-  for (int p4 = 0; p4 < 4; ++p4) {
-    const uint32_t piece = (((uint32_t)(sub * 4 + p4)) ^ swz) << 4;
+  for (int p4 = 0; p4 < NP4; ++p4) {
+    const uint32_t piece = (((uint32_t)(piece0 + p4)) ^ swz) << 4;
     float wa[8];
     if (EPI == 2) {
       const float4 a0 = lds128(wa_addr + (uint32_t)(c0 + p4 * 8) * 4u);
@@ -306,12 +307,12 @@ __device__ __forceinline__ void bwd_cols(const uint32_t (&r)[32], const int c, c
       uint64_t x = pack64(r[p4 * 8 + 2 * e], r[p4 * 8 + 2 * e + 1]);
       if (EPI == 2) x = fma_f32x2(ds2, pack64(__float_as_uint(wa[2 * e]), __float_as_uint(wa[2 * e + 1])), x);
       uint32_t v = cvt_bf16x2<false>(x);
-      if (EPI >= 1) v &= ((bits >> (p4 * 4 + e)) & 0x00010001u) * 0xFFFFu;
+      if (EPI >= 1) v &= ((bits >> (bit0 + p4 * 4 + e)) & 0x00010001u) * 0xFFFFu;
       pk[e] = v;
     }
     sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
   }
-  fence_proxy_async_smem();
+  if (NP4 == 4) fence_proxy_async_smem();  // quarter steps: the caller fences after issuing the next TMEM load
 }
 
 // Branch-free sin/cos for the fused encoder: three-term Cody-Waite reduction by pi/2 and the usual degree-7/8 minimax
@@ -426,7 +427,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     }
     for (int i = 0; i < 4; ++i) mbar_init(&tfull[i], 1);
     for (int i = 0; i < 2; ++i) mbar_init(&tempty[i], kEpiWarps);
-    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], (MODE == 0 && NMX_EPI_QUARTER) ? kEpiWarps : kEpiWarps / 2);
+    for (int i = 0; i < 4; ++i) mbar_init(&act_ready[i], NMX_EPI_QUARTER ? kEpiWarps : kEpiWarps / 2);
     mbar_init(x0pos_full, 1);
     mbar_init(x0pos_empty, 1);
     mbar_init(x0dir_full, 1);
@@ -849,11 +850,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       const uint32_t wrgb_addr = smem_u32(s_wrgb);  // w_rgb [3][128] fp32
       const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
       const bool no_mask = (prm.dbg & 8) != 0;  // experiment: skip the saved-activation reads
-      const int c_a = part >> 1, sub_a = part & 1;  // step A: this warp's chunk / 32-column sub-block of d_hd
       uint32_t lcount = 0, scount = 0;
       uint32_t mstep = 0;  // masked steps so far (step A + masked layers): slot = mstep & 1, parity = (mstep >> 1) & 1
       const uint32_t bits_base = smem_u32(s_bits) + (uint32_t)row_local * 32u;
-      const int col0 = c_a * 64 + sub_a * 32;       // half-0 column of a [P,256] tensor; half 1 = col0 + 128
       auto ld_bits = [&](uint32_t slot, int w) -> uint32_t {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(bits_base + slot * kBitsBytes + (uint32_t)w * 4u) : "memory");
@@ -866,42 +865,48 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
         float4 dr = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (row_ok) dr = __ldg(reinterpret_cast<const float4*>(prm.d_out) + row);
         // ---- step A: d_hd = (d_rgb W_rgb) * [hd > 0]  -> chunks 0,1 (A operand of the dir-layer data gradient)
+        // Quarter layout as in the layers below: every warp takes 16 columns of chunk 0, then 16 columns of chunk 1.
         if (scount > 0) mbar_wait(store_done, (scount - 1) & 1);
         {
-          uint32_t bits = ~0u;
+          uint32_t bw[2] = {~0u, ~0u};
           if (!no_mask) {
             mbar_wait(&bits_full[mstep & 1u], (mstep >> 1) & 1u);
-            bits = ld_bits(mstep & 1u, part);
+            bw[0] = ld_bits(mstep & 1u, part >> 1);
+            bw[1] = ld_bits(mstep & 1u, 2 + (part >> 1));
           }
-          const uint32_t so = act_row_addr + (uint32_t)c_a * kChunkBytes;
 #pragma unroll
-          for (int p4 = 0; p4 < 4; ++p4) {
-            const int j = part * 32 + p4 * 8;
-            const uint32_t piece = (((uint32_t)(sub_a * 4 + p4)) ^ swz) << 4;
-            float v[8];
+          for (int st = 0; st < 2; ++st) {
+            const uint32_t so = act_row_addr + (uint32_t)st * kChunkBytes;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const float4 w0 = lds128(wrgb_addr + (uint32_t)(0 * 128 + j + hh * 4) * 4u);
-              const float4 w1 = lds128(wrgb_addr + (uint32_t)(1 * 128 + j + hh * 4) * 4u);
-              const float4 w2 = lds128(wrgb_addr + (uint32_t)(2 * 128 + j + hh * 4) * 4u);
-              v[hh * 4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
-              v[hh * 4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
-              v[hh * 4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
-              v[hh * 4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+            for (int p4 = 0; p4 < 2; ++p4) {
+              const int j = st * 64 + part * 16 + p4 * 8;
+              const uint32_t piece = (((uint32_t)(2 * part + p4)) ^ swz) << 4;
+              float v[8];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float4 w0 = lds128(wrgb_addr + (uint32_t)(0 * 128 + j + hh * 4) * 4u);
+                const float4 w1 = lds128(wrgb_addr + (uint32_t)(1 * 128 + j + hh * 4) * 4u);
+                const float4 w2 = lds128(wrgb_addr + (uint32_t)(2 * 128 + j + hh * 4) * 4u);
+                v[hh * 4 + 0] = dr.x * w0.x + dr.y * w1.x + dr.z * w2.x;
+                v[hh * 4 + 1] = dr.x * w0.y + dr.y * w1.y + dr.z * w2.y;
+                v[hh * 4 + 2] = dr.x * w0.z + dr.y * w1.z + dr.z * w2.z;
+                v[hh * 4 + 3] = dr.x * w0.w + dr.y * w1.w + dr.z * w2.w;
+              }
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]) &
+                        (((bw[st] >> (8 * (part & 1) + p4 * 4 + e)) & 0x00010001u) * 0xFFFFu);
+              sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
             }
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              pk[e] = pack_bf16(v[2 * e], v[2 * e + 1]) & (((bits >> (p4 * 4 + e)) & 0x00010001u) * 0xFFFFu);
-            sts128(so + piece, pk[0], pk[1], pk[2], pk[3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&act_ready[st]);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&act_ready[c_a]);
-            if (!no_mask) mbar_arrive(&bits_empty[mstep & 1u]);
+          if (!no_mask) {
+            if (lane == 0) mbar_arrive(&bits_empty[mstep & 1u]);
+            ++mstep;
           }
-          if (!no_mask) ++mstep;
         }
         ++scount;
         for (int l = 0; l < NL; ++l, ++lcount, ++scount) {
@@ -910,48 +915,45 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           const int epi = no_mask ? (prm.L[l].epi == 2 ? 2 : 0) : prm.L[l].epi;
           const bool masked = prm.L[l].epi >= 1 && !no_mask;
           const uint32_t slot = mstep & 1u;
+          const int nsteps = prm.L[l].N / 64;
           // the TMA stores of the previous step's chunks must have finished reading shared memory
           mbar_wait(store_done, (scount - 1) & 1);
           const uint32_t tacc = tmem_base + (uint32_t)(as * 256) + ((uint32_t)(q * 32) << 16);
-          uint32_t bits0 = 0, bits1 = 0;
+          uint32_t bw[4] = {0u, 0u, 0u, 0u};
           if (masked) {
             mbar_wait(&bits_full[slot], (mstep >> 1) & 1u);
-            bits0 = ld_bits(slot, part);
-            bits1 = ld_bits(slot, 4 + part);
+#pragma unroll
+            for (int st = 0; st < 4; ++st) bw[st] = ld_bits(slot, 2 * st + (part >> 1));
             ++mstep;
           }
-          // ---- half 0 (chunks 0,1)
+          // ---- four quarter steps: one 64-column chunk per step, 16 columns per warp; the TMEM load of step s+1 is
+          //      issued before the proxy fence of step s
           mbar_wait(&tfull[as * 2 + 0], aphase);
           trace(tr_on, 1, it, l, 0);
           tc_fence_after();
-          {
-            const int c = c_a;
-            uint32_t r[32];
-            tmem_ld_32x32(tacc + (uint32_t)col0, r);
-            tmem_ld_wait_regs<32>(r);
-            if (epi == 2) bwd_cols<2>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, dr.w);
-            else if (epi == 1) bwd_cols<1>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, 0.0f);
-            else bwd_cols<0>(r, c, col0, sub_a, act_row_addr, swz, bits0, wa_addr, 0.0f);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&act_ready[c]);
-          }
-          // ---- half 1 (chunks 2,3)
-          mbar_wait(&tfull[as * 2 + 1], aphase);
-          tc_fence_after();
-          {
-            const int c = 2 + c_a;
-            uint32_t r[32];
-            tmem_ld_32x32(tacc + (uint32_t)(col0 + 128), r);
-            tmem_ld_wait_regs<32>(r);
-            if (epi == 2) bwd_cols<2>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, dr.w);
-            else if (epi == 1) bwd_cols<1>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, 0.0f);
-            else bwd_cols<0>(r, c, col0 + 128, sub_a, act_row_addr, swz, bits1, wa_addr, 0.0f);
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&act_ready[c]);
-              if (masked) mbar_arrive(&bits_empty[slot]);  // the slot can be refilled
+          uint32_t r[16];
+          tmem_ld_32x16(tacc + (uint32_t)(part * 16), r);
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            if (st < nsteps) {
+              const int c0 = st * 64 + part * 16;
+              tmem_ld_wait_regs<16>(r);
+              if (epi == 2) bwd_cols<2, 2>(r, st, c0, 2 * part, 8 * (part & 1), act_row_addr, swz, bw[st], wa_addr, dr.w);
+              else if (epi == 1) bwd_cols<1, 2>(r, st, c0, 2 * part, 8 * (part & 1), act_row_addr, swz, bw[st], wa_addr, 0.0f);
+              else bwd_cols<0, 2>(r, st, c0, 2 * part, 8 * (part & 1), act_row_addr, swz, bw[st], wa_addr, 0.0f);
+            }
+            if (st == 1) {
+              mbar_wait(&tfull[as * 2 + 1], aphase);
+              tc_fence_after();
+            }
+            if (st < nsteps) {
+              if (st + 1 < nsteps) tmem_ld_32x16(tacc + (uint32_t)((st + 1) * 64 + part * 16), r);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&act_ready[st]);
             }
           }
+          if (masked && lane == 0) mbar_arrive(&bits_empty[slot]);  // the slot can be refilled
           trace(tr_on, 1, it, l, 2);
           tc_fence_before();
           __syncwarp();
