@@ -80,6 +80,7 @@ struct GemmArgs {
   const float* row_vec;   // optional rank-1 term row_vec[m*row_stride] * col_vec[n] added before the mask
   int row_stride;
   const float* col_vec;
+  int accum;              // fp32 output only: D += result (the tile owns its rows: plain read-modify-write)
 };
 
 template <int BN, int STAGES>
@@ -248,6 +249,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               for (int e = 0; e < 4; ++e) {
                 float x = __uint_as_float(r[k4 * 4 + e]) + s_bias[c0 + k4 * 4 + e] + rv * s_colv[c0 + k4 * 4 + e];
                 v[e] = args.relu ? fmaxf(x, 0.0f) : x;
+              }
+              if (args.accum) {
+                const float4 o = dp[k4];
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
               }
               dp[k4] = make_float4(v[0], v[1], v[2], v[3]);
             }
@@ -569,7 +574,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   a.a0_col = g.a0_col; a.a0_k = g.a0_k; a.a1_col = g.a1_col; a.a1_k = (g.A1 ? g.a1_k : 0);
   a.b_col = g.b_col; a.M = (int)g.M; a.N = g.N; a.bias = g.bias; a.D = g.D; a.ldd = g.ldd; a.out_fp32 = g.out_fp32;
   a.relu = g.relu; a.use_mask = g.mask != nullptr; a.mask_col = g.mask_col; a.d_col = g.d_col; a.row_vec = g.row_vec;
-  a.row_stride = g.row_stride; a.col_vec = g.col_vec;
+  a.row_stride = g.row_stride; a.col_vec = g.col_vec; a.accum = g.accum;
   int tiles = (int)((g.M + BM - 1) / BM);
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   prof_begin(0, 2.0 * (double)g.M * g.N * (g.a0_k + a.a1_k), stream);

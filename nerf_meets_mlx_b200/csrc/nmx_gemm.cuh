@@ -15,6 +15,7 @@ struct GemmDesc {
   int d_cols, d_col;                                  // D tensor width (0 = N) and first output column
   const void* mask; int ldmask; int mask_cols, mask_col;  // output *= (mask > 0); mask tensor [M, mask_cols]
   const float* row_vec; int row_stride; const float* col_vec;  // + row_vec[m] * col_vec[n] before the mask
+  int accum;                                          // fp32 output: D += result
 };
 
 // dW[M, w_col + (0..n_valid)) += dY[P, dy_col + (0..M))^T * X[P, x_col + (0..N))

@@ -44,6 +44,7 @@ struct nmx_mlp_plan {
   std::vector<int> wf_k;                // padded K of each trunk layer
   int64_t wf_feat, wt_feat, wf_dir, wt_dir;
   int wf_dir_k;
+  int64_t wt_in;  // [pos_pad, 2W]: transposed position-input columns of layer 0 (k < W) and of the skip layer (k >= W)
   int64_t weights_bytes;
   // activation region (offsets relative to its start; depend on capacity)
   int64_t act_points_train, act_points_infer;
@@ -116,7 +117,7 @@ pack_weights_kernel(const float* __restrict__ params, uint8_t* __restrict__ ws, 
       dst[(size_t)r * sg.dst_ld + sg.dst_col0 + c] = __float2bfloat16_rn(src[(size_t)r * sg.src_ld + sg.src_col0 + c]);
     } else {
       int c = i / sg.rows, r = i - c * sg.rows;
-      dst[(size_t)c * sg.dst_ld + r] = __float2bfloat16_rn(src[(size_t)r * sg.src_ld + sg.src_col0 + c]);
+      dst[(size_t)c * sg.dst_ld + sg.dst_col0 + r] = __float2bfloat16_rn(src[(size_t)r * sg.src_ld + sg.src_col0 + c]);
     }
   }
 }
@@ -510,6 +511,7 @@ extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, 
     p->wf_dir = wb; wb += align256((int64_t)(p->W / 2) * p->wf_dir_k * 2);
     p->wt_dir = wb; wb += align256((int64_t)p->W * (p->W / 2) * 2);
   }
+  p->wt_in = wb; wb += align256((int64_t)p->pos_pad * 2 * p->W * 2);
   // scratch for padded wgrad outputs (fp32 [W, 64]) and per-ray dir PE
   p->weights_bytes = align256(wb);
   *out = p;
@@ -554,8 +556,10 @@ extern "C" int nmx_mlp_load_params(nmx_mlp_plan* p, const float* params, void* w
     bool skip_in = (r.in == W + p->in_pos);
     if (l == 0) {
       add(r.w_off, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos, 0);
+      add(r.w_off, r.in, 0, p->wt_in, 2 * W, 0, W, p->in_pos, 1);
     } else if (skip_in) {
       add(r.w_off, r.in, 0, p->wf_off[l], p->wf_k[l], 0, W, p->in_pos, 0);
+      add(r.w_off, r.in, 0, p->wt_in, 2 * W, W, W, p->in_pos, 1);
       add(r.w_off, r.in, p->in_pos, p->wf_off[l], p->wf_k[l], p->pos_pad, W, W, 0);
       add(r.w_off, r.in, p->in_pos, p->wt_off[l], W, 0, W, W, 1);
     } else {
@@ -917,8 +921,22 @@ extern "C" int nmx_mlp_debug_layout(const nmx_mlp_plan* p, int64_t* out, int n) 
 }
 
 // ================================================================================================ backward
+static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, const float* d_out, float* d_params,
+                        float* d_input, int64_t P, void* stream_);
+
 extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params, const float* d_out,
                            float* d_params, int64_t P, void* stream_) {
+  return mlp_bwd_impl(p, workspace, params, d_out, d_params, nullptr, P, stream_);
+}
+
+extern "C" int nmx_mlp_bwd_input(nmx_mlp_plan* p, void* workspace, const float* params, const float* d_out,
+                                 float* d_params, float* d_input, int64_t P, void* stream_) {
+  NMX_CHECK_ARG(d_input != nullptr, "d_input non-null");
+  return mlp_bwd_impl(p, workspace, params, d_out, d_params, d_input, P, stream_);
+}
+
+static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, const float* d_out, float* d_params,
+                        float* d_input, int64_t P, void* stream_) {
   NMX_CHECK_ARG(p && workspace && params && d_out && d_params, "plan, workspace, params, d_out, d_params non-null");
   NMX_CHECK_ARG(P >= 0 && P <= p->max_points, "0 <= P <= max_points");
   cudaStream_t s = (cudaStream_t)stream_;
@@ -942,6 +960,19 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
     g.P = P; g.M = M; g.N = N; g.dW = dW; g.ldw = ldw; g.w_col = w_col; g.n_valid = n_valid; g.db = db;
     return launch_wgrad(g, s);
   };
+
+  // gradient w.r.t. the (already encoded) position inputs: d_x[rows, pos_pad] (+)= dY[rows, W] * W_l[:, :in_pos]
+  // (fp32, columns >= in_pos are zero); k_col selects layer 0 (0) or the skip layer (W) inside the packed wt_in
+  auto input_grad = [&](const bf16* dY, int64_t r0, int64_t rows, int k_col, bool accumulate) {
+    GemmDesc g{};
+    g.A0 = dY; g.a0_rows = rows; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
+    g.B = c.ws + p->wt_in; g.b_rows = p->pos_pad; g.b_cols = 2 * W; g.b_ld = 2 * W; g.b_col = k_col;
+    g.M = rows; g.N = p->pos_pad; g.D = d_input + r0 * p->pos_pad; g.ldd = p->pos_pad; g.out_fp32 = 1;
+    g.accum = accumulate ? 1 : 0;
+    return launch_gemm(g, s);
+  };
+  const int skip_l = p->cfg.skip_layer >= 0 ? p->cfg.skip_layer + 1 : -1;  // the layer whose input is [x_pos, h]
+  if (d_input != nullptr && p->pos_pad > 256) { set_error("input gradient: encoded width <= 256"); return NMX_E_UNSUPPORTED; }
 
   if (getenv("NMX_DEBUG_SYNC")) {
     cudaError_t e0 = cudaDeviceSynchronize();
@@ -1048,6 +1079,14 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
         }
       }
     }
+    if (d_input != nullptr) {  // dY_0 and the skip layer's dY are still in their slots
+      bool acc = false;
+      if (skip_l > 0 && skip_l < p->D) {
+        if ((rc = input_grad(c.G(skip_l), 0, P, W, false))) return rc;
+        acc = true;
+      }
+      if ((rc = input_grad(c.G(0), 0, P, 0, acc))) return rc;
+    }
     {  // feature / dir-layer weight gradients from G (after every chunk's wgrad has been accumulated)
       cudaStream_t sw = K > 1 ? s2 : s;
       fold_feature_grads_kernel<<<W / 2 + W, 256, W * sizeof(float), sw>>>(
@@ -1120,6 +1159,10 @@ extern "C" int nmx_mlp_bwd(nmx_mlp_plan* p, void* workspace, const float* params
         if ((rc = wgrad(dY, W, (c.H(l - 1) + r0 * W), W, 0, W, W, W, dW, r.in, p->in_pos, db))) return rc;
       } else {
         if ((rc = wgrad(dY, W, (c.H(l - 1) + r0 * W), W, 0, W, W, W, dW, r.in, 0, db))) return rc;
+      }
+      if (d_input != nullptr) {
+        if (l == skip_l && l > 0) { if ((rc = input_grad(dY, r0, rows, W, false))) return rc; }
+        if (l == 0) { if ((rc = input_grad(dY, r0, rows, 0, skip_l > 0 && skip_l < p->D))) return rc; }
       }
       if (l >= 1) {
         GemmDesc g{};

@@ -27,7 +27,10 @@ class _LinearView:
 class _MLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flat, model, enc_kind, x_or_rays, z, bands, B, n):
-        need_grad = bool(ctx.needs_input_grad[0])  # grad mode is off inside Function.forward
+        # grad mode is off inside Function.forward; an already-encoded input (enc_kind 0) may itself need a gradient:
+        # a learnable encoder in front of the MLP (the hash grid) gets it as the reference's autograd would give it
+        ctx.input_grad = bool(enc_kind == 0 and ctx.needs_input_grad[3])
+        need_grad = bool(ctx.needs_input_grad[0]) or ctx.input_grad
         out = model._fwd_raw(enc_kind, x_or_rays, z, bands, B, n, save=need_grad)
         ctx.model = model
         ctx.P = B * n
@@ -35,6 +38,9 @@ class _MLPFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        if ctx.input_grad:
+            g, d_x = ctx.model._bwd_raw(d_out.contiguous(), ctx.P, want_input_grad=True)
+            return g, None, None, d_x, None, None, None, None
         g = ctx.model._bwd_raw(d_out.contiguous(), ctx.P)
         return g, None, None, None, None, None, None, None
 
@@ -189,12 +195,23 @@ class NeRF(torch.nn.Module):
                L.i32(stride), L.ptr(z), L.ptr(bands), L.ptr(out), L.i64(B), L.i32(n), L.i32(1 if save else 0), L.stream())
         return out
 
-    def _bwd_raw(self, d_out, P, out=None):
+    def _bwd_raw(self, d_out, P, out=None, want_input_grad=False):
         if not self._ws_train:
             raise L.NmxError("nmx_mlp_bwd needs a forward with saved activations on this model first")
         g = out if out is not None else torch.empty_like(self.flat.data)
-        L.call("nmx_mlp_bwd", self._plan, L.ptr(self._ws), L.ptr(self.flat), L.ptr(d_out), L.ptr(g), L.i64(P), L.stream())
-        return g
+        if not want_input_grad:
+            L.call("nmx_mlp_bwd", self._plan, L.ptr(self._ws), L.ptr(self.flat), L.ptr(d_out), L.ptr(g), L.i64(P), L.stream())
+            return g
+        # gradient w.r.t. the encoded position inputs [P, pos_pad] fp32; view-direction inputs get zeros (no learnable
+        # encoder feeds them in the reference)
+        pos_pad = (self.channel_input_pos + 63) // 64 * 64
+        d_pad = torch.empty((P, pos_pad), dtype=torch.float32, device=g.device)
+        L.call("nmx_mlp_bwd_input", self._plan, L.ptr(self._ws), L.ptr(self.flat), L.ptr(d_out), L.ptr(g), L.ptr(d_pad),
+               L.i64(P), L.stream())
+        d_x = d_pad[:, :self.channel_input_pos]
+        if self.is_use_view_directions and self.channel_input_dir > 0:
+            d_x = torch.cat([d_x, torch.zeros((P, self.channel_input_dir), dtype=torch.float32, device=g.device)], dim=-1)
+        return g, d_x.contiguous()
 
     # ---------------------------------------------------------------- reference API
     def forward(self, x):

@@ -113,7 +113,7 @@ def image_step(model, opt, X_int, y, n_freqs=10, min_exp=0.0, max_exp=8.0):
     g = _grads(model, loss)
     model.requires_grad_(False)
     opt.update(model, g)
-    return float(loss), g
+    return float(loss.detach()), g
 
 
 def psnr(mse):
