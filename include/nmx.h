@@ -191,6 +191,8 @@ int nmx_profile_report(int kind, double* total_ms, double* total_flops, int64_t*
  * nmx_chain_trace_read: copies the (clock, ns) event trace the fused MLP chain records for CTA 0 when the environment
  * variable NMX_CHAIN_DBG has bit 2 set. */
 int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream, int mode);
+/* TMEM -> register read-rate probe (tcgen05.ld.32x32b.x16 / .x32): out[2*cta] = clocks, out[2*cta+1] = bytes read */
+int nmx_diag_tmem_ld_rate(int iters, int warps, int mode, int batch, int ctas, long long* out, void* stream);
 int nmx_chain_trace_read(long long* out, int n);
 /* byte offsets of the training workspace regions: out[12] = {activation base, x0, h0, h stride, feature, hd, g0, g stride,
  * ghd, relu sign bits, capacity (points), x0 columns}; region offsets are relative to the activation base. */

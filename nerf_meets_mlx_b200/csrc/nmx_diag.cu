@@ -77,7 +77,63 @@ mma_rate_kernel(int N, int iters, int n_slabs, int mode, long long* out) {
   if (threadIdx.x < 32) tmem_dealloc<512>(tmem_base);
 }
 
+// TMEM -> register read-rate probe: `warps` warps (warp w reads lane quadrant w & 3) issue `iters` back-to-back
+// tcgen05.ld.32x32b.x16 (mode 0) or .x32 (mode 1) over the 512 allocated columns, one tcgen05.wait::ld per `batch`
+// loads; out[0] = clocks for the whole CTA, out[1] = bytes read.
+__global__ void __launch_bounds__(1024, 1)
+tmem_ld_rate_kernel(int iters, int mode, int batch, long long* out) {
+  __shared__ uint32_t tmem_ptr;
+  __shared__ long long t0s, t1s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) tmem_alloc<512>(&tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) t0s = clock64();
+  __syncthreads();
+  const int cols = mode ? 32 : 16;
+  for (int i = 0; i < iters; i += batch) {
+    for (int b = 0; b < batch; ++b) {
+      const uint32_t col = (uint32_t)(((i + b) * cols + (warp >> 2) * 64) & 511) & ~(uint32_t)(cols - 1);
+      if (mode) {
+        uint32_t r[32];
+        tmem_ld_32x32(base + (col & 480u), r);
+        if (b == batch - 1) tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc ^= r[k];
+      } else {
+        uint32_t r[16];
+        tmem_ld_32x16(base + (col & 496u), r);
+        if (b == batch - 1) tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc ^= r[k];
+      }
+    }
+  }
+  tmem_ld_wait();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    t1s = clock64();
+    out[blockIdx.x * 2 + 0] = t1s - t0s;
+    out[blockIdx.x * 2 + 1] = (long long)iters * cols * 4 * 32 * (blockDim.x >> 5);
+  }
+  if (acc == 0x12345u && lane == 0) out[0] = -1;  // keep the loads alive
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_ptr);
+}
+
 }  // namespace
+
+extern "C" int nmx_diag_tmem_ld_rate(int iters, int warps, int mode, int batch, int ctas, long long* out, void* stream) {
+  NMX_CHECK_ARG(out && iters > 0 && warps >= 1 && warps <= 32 && batch >= 1 && ctas > 0, "iters > 0; 1 <= warps <= 32; batch >= 1");
+  tmem_ld_rate_kernel<<<ctas, warps * 32, 0, (cudaStream_t)stream>>>(iters, mode, batch, out);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
 
 // out: int64 [2 * ctas] device buffer = (SM clocks, nanoseconds) per CTA
 extern "C" int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, void* stream, int mode) {
