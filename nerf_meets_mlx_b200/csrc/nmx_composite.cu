@@ -40,9 +40,8 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ zr, const f
   if (!valid) delta = 0.0f;
 }
 
-// NCHUNK > 0: n <= 32*NCHUNK and every load of the ray is issued before the first scan (the chunk loop is unrolled
-// over register arrays), so a warp keeps its whole ray in flight; NCHUNK == 0: any n, one chunk at a time.
-template <int NCHUNK>
+// One chunk of 32 samples at a time (32 registers, full occupancy).  Issuing all of a ray's loads up front from
+// register arrays was measured slower on B200 (n = 192: 116 us vs 81 us per 65536 rays): occupancy wins here.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      int d_stride, const float* __restrict__ noise, float noise_std, int white_bkgd,
@@ -59,25 +58,11 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     float norm = ray_norm(rays_d + b * d_stride);
     float carry = 0.0f;
     float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
-    constexpr int NA = NCHUNK > 0 ? NCHUNK : 1;
-    float zi_[NA], delta_[NA];
-    float4 rv_[NA];
-    bool valid_[NA];
-    if (NCHUNK > 0) {
-#pragma unroll
-      for (int c = 0; c < NA; ++c)
-        load_chunk(zr, rawr, noiser, noise_std, n, c, lane, norm, zi_[c], delta_[c], rv_[c], valid_[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < (NCHUNK > 0 ? NCHUNK : nchunks); ++c) {
+    for (int c = 0; c < nchunks; ++c) {
       float zi, delta;
       float4 rv;
       bool valid;
-      if (NCHUNK > 0) {
-        zi = zi_[c]; delta = delta_[c]; rv = rv_[c]; valid = valid_[c];
-      } else {
-        load_chunk(zr, rawr, noiser, noise_std, n, c, lane, norm, zi, delta, rv, valid);
-      }
+      load_chunk(zr, rawr, noiser, noise_std, n, c, lane, norm, zi, delta, rv, valid);
       float tau = __fmul_rn(delta, rv.w);
       // exclusive prefix must not see the (huge) last-bin tau of the final sample: mask it out of the scan
       int i = c * 32 + lane;
@@ -216,15 +201,8 @@ extern "C" int nmx_composite_fwd(const float* raw, const float* z, const float* 
   NMX_CHECK_ARG(raw && z && rays_d, "raw, z, rays_d must be non-null");
   if (raw_noise_std <= 0.0f) noise = nullptr;
   int blocks = grid_for(B, kWarpsPerBlock, 8);
-  const int nch = (n + 31) / 32;
-#define NMX_FWD(NC)                                                                        \
-  composite_fwd_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(      \
-      raw, z, rays_d, d_stride, noise, raw_noise_std, white_bkgd, rgb, disp, acc, weights, depth, B, n)
-  // measured on B200 (scripts/bench_aux.py): the chunk-loop form (32 registers, full occupancy) beats the
-  // all-loads-up-front variants (n = 192: 81 us vs 116 us per 65536 rays), so those stay compiled but unused
-  (void)nch;
-  NMX_FWD(0);
-#undef NMX_FWD
+  composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      raw, z, rays_d, d_stride, noise, raw_noise_std, white_bkgd, rgb, disp, acc, weights, depth, B, n);
   NMX_LAUNCH_CHECK();
   return 0;
 }
