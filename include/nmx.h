@@ -170,6 +170,9 @@ int nmx_mlp_bwd_input(nmx_mlp_plan* plan, void* workspace, const float* params, 
  * D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]);  A,B bf16 row-major (K-major), D bf16 or fp32. */
 int nmx_gemm_bf16(const void* A, const void* Bm, const float* bias, void* D, int64_t M, int N, int K,
                   int relu, int d_is_fp32, void* stream);
+/* the same product on CTA pairs (tcgen05 cta_group::2, M = 256 tiles, each CTA stages half of the weight slab):
+ * D[M, 256] fp32 = A[M, K] * B[256, K]^T; K % 64 == 0; max_pairs caps the number of clusters (0 = all SM pairs). */
+int nmx_gemm_pair_bf16(const void* A, const void* Bm, float* D, int64_t M, int K, int max_pairs, void* stream);
 /* dW[M,N] (fp32, accumulated: caller zeroes) += dY[P,M]^T * X[P,N]; bf16 row-major inputs, read as MN-major
  * UMMA operands (no transposes); M % 64 == 0, N % 64 == 0, N <= 256.  Optional db[M] (fp32, accumulated) += column
  * sums of dY (the bias gradient), computed by one extra N=16 MMA against a constant all-ones operand tile. */

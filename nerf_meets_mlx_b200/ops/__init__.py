@@ -228,6 +228,17 @@ def gemm_bf16(A, B, bias=None, relu=False, out_fp32=False):
     return D
 
 
+def gemm_pair_bf16(A, B, max_pairs=0):
+    """D[M,256] fp32 = A[M,K] @ B[256,K].T on CTA pairs (tcgen05 cta_group::2; unit-test hook)."""
+    require_cuda(A, B)
+    M, K = A.shape
+    if B.shape != (256, K):
+        raise ValueError("B must be [256, K]")
+    D = torch.empty((M, 256), dtype=torch.float32, device=A.device)
+    call("nmx_gemm_pair_bf16", ptr(A), ptr(B), ptr(D), i64(M), i32(K), i32(max_pairs), stream())
+    return D
+
+
 def wgrad_bf16(dY, X, want_db=False):
     """dW[M,N] = dY[P,M].T @ X[P,N] in fp32 (tcgen05 kernel, MN-major operands; unit-test hook).
     want_db: also return db[M] = column sums of dY (bias gradient) from the fused ones-column MMA."""

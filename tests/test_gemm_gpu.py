@@ -51,3 +51,15 @@ def test_colsum(ops):
     ref = Y.float().sum(0)
     out = ops.colsum_bf16(Y)
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,K,max_pairs", [(256, 64, 1), (1000, 256, 0), (256 * 74 * 3 + 77, 320, 0)])
+def test_gemm_cta_pair(ops, M, K, max_pairs):
+    """tcgen05 cta_group::2 building block: both CTAs of a pair stage their rows of A and their half of B, the leader
+    issues M = 256 MMAs, each CTA reads back its own 128 accumulator rows (ragged last tile, several tiles per pair)."""
+    torch.manual_seed(M)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.randn(256, K, device="cuda").bfloat16()
+    D = ops.gemm_pair_bf16(A, B, max_pairs)
+    ref = A.float() @ B.float().T
+    assert float((D - ref).abs().max() / ref.abs().max()) < 1e-5
