@@ -72,4 +72,20 @@ struct ChainMaps {
 int launch_chain_fwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream);
 int launch_chain_bwd(const ChainMaps& maps, const ChainParams& prm, cudaStream_t stream);
 
+// Inference forward of the 8 x 256 view-dir net on CTA pairs with two tiles in ping-pong (nmx_chain2.cu).
+struct Chain2Launch {
+  long long P;                 // points of this launch
+  const float* params;         // packed fp32 parameters
+  float* out;                  // [P, 4] fp32
+  const void* w_ptr[10];       // bf16 weights [N_l, K_l] of the 8 trunk layers, feature layer, dir layer
+  int w_k[10];                 // padded K (row length) of each
+  int bias_off[10];
+  int alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;
+  const float* rays; int ray_stride; const float* z;
+  long long p0; int n_per_ray; int n_freqs_dir;
+  int dir_w_off, dir_ldw;      // fp32 dir-layer weight [128, dir_ldw]; its columns 256.. multiply PE(dir)
+  float* dir_bias;             // scratch [rays of this launch, 128] fp32
+};
+int launch_chain2(const Chain2Launch& a, cudaStream_t stream);
+
 }  // namespace nmx

@@ -865,6 +865,34 @@ int backward_chain(const Ctx& c, int64_t row0, int64_t P, int64_t cap, const flo
   return launch_chain_bwd(maps, prm, st);
 }
 
+// Inference of the reference's 8 x 256 view-dir net straight from rays: CTA pairs, two tiles in ping-pong (nmx_chain2.cu).
+// EXPERIMENTAL, opt-in with NMX_ENABLE_CHAIN2=1: numerically validated (tests/test_chain_gpu.py) but on B200 it is
+// still slower than the one-tile chain (1.89 ms vs 1.72 ms for 8192 x 192 points; DESIGN.md 3.1 has the breakdown).
+bool chain2_ok(const nmx_mlp_plan* p, int enc_kind, int n) {
+  static int off = -1;
+  if (off < 0) off = getenv("NMX_ENABLE_CHAIN2") ? 0 : 1;
+  return !off && chain_eligible(p) && p->cfg.use_viewdirs && p->W == 256 && p->D == 8 && p->cfg.skip_layer == 4 &&
+         p->pos_pad == 64 && p->dir_pad == 64 && enc_fused_ok(p, enc_kind) && n >= 8;
+}
+
+int forward_chain2(const Ctx& c, int64_t npts, float* out, const EncIn& enc) {
+  const nmx_mlp_plan* p = c.p;
+  Chain2Launch a;
+  memset(&a, 0, sizeof(a));
+  a.P = npts; a.params = c.params; a.out = out;
+  for (int l = 0; l < 8; ++l) {
+    a.w_ptr[l] = c.ws + p->wf_off[l]; a.w_k[l] = p->wf_k[l]; a.bias_off[l] = (int)p->trunk[l].b_off;
+  }
+  a.w_ptr[8] = c.ws + p->wf_feat; a.w_k[8] = p->W; a.bias_off[8] = (int)p->feat.b_off;
+  a.w_ptr[9] = c.ws + p->wf_dir; a.w_k[9] = p->wf_dir_k; a.bias_off[9] = (int)p->dir.b_off;
+  a.alpha_w_off = (int)p->alpha.w_off; a.alpha_b_off = (int)p->alpha.b_off;
+  a.rgb_w_off = (int)p->rgb.w_off; a.rgb_b_off = (int)p->rgb.b_off;
+  a.rays = enc.rays; a.ray_stride = enc.ray_stride; a.z = enc.z; a.p0 = enc.p0; a.n_per_ray = enc.n;
+  a.n_freqs_dir = p->cfg.n_freqs_dir; a.dir_w_off = (int)p->dir.w_off; a.dir_ldw = p->dir.in;
+  a.dir_bias = (float*)(c.ws + p->weights_bytes);  // per-ray scratch: 512 B per ray <= 128 B per point for n >= 4
+  return launch_chain2(a, c.s);
+}
+
 }  // namespace
 
 extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
@@ -900,8 +928,12 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   c.al = act_layout(p, cap, false);
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t npts = P - p0 < cap ? P - p0 : cap;
-    if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
     EncIn ei{x_or_rays, ray_stride, z, p0, n};
+    if (chain2_ok(p, enc_kind, n)) {
+      if ((rc = forward_chain2(c, npts, out + p0 * out_cols, ei))) return rc;
+      continue;
+    }
+    if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
     if (chain_eligible(p)) rc = forward_chain(c, npts, cap, out + p0 * out_cols, out_cols, &ei);
     else rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols);
     if (rc) return rc;

@@ -14,6 +14,7 @@
 //   tempty[a] (leader's copy): 8 arrivals = 4 epilogue warps x 2 CTAs (CTA 1 arrives remotely through mapa).
 #include "nmx_common.cuh"
 #include "nmx_sm100.cuh"
+#include <cstdlib>
 
 using namespace nmx;
 using namespace nmx::sm100;
@@ -23,62 +24,11 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kThreads = 192;            // warp 0 TMA, warp 1 MMA (leader only), warps 2..5 epilogue
 constexpr int kStageBytes = 2 * 16384;   // A [128 x 64] + B half [128 x 64] bf16
-constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-// both CTAs call this; completion bytes land on the LEADER's barrier (same offset, peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)m), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs once all prior MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-               : "memory");
-}
-
 struct PairArgs {
   int M, K;
   float* D;
   int ldd;
+  int no_store;  // experiment (NMX_PAIR_NOSTORE): skip the fp32 output stores to time the TMA + MMA pipeline alone
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -172,7 +122,7 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + as * 256 + c0 + ((uint32_t)(q * 32) << 16), r);
         tmem_ld_wait();
-        if (row < args.M) {
+        if (row < args.M && !(args.no_store && r[0] != 0x7fc00001u)) {
           float4* dp = reinterpret_cast<float4*>(args.D + (size_t)row * args.ldd + c0);
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4)
@@ -202,6 +152,7 @@ extern "C" int nmx_gemm_pair_bf16(const void* A, const void* Bm, float* D, int64
   if ((rc = make_tmap_bf16_2d(&tB, Bm, 256, (uint64_t)K, (uint64_t)K, 128))) return rc;
   PairArgs a;
   a.M = (int)M; a.K = K; a.D = D; a.ldd = 256;
+  a.no_store = getenv("NMX_PAIR_NOSTORE") ? 1 : 0;
   const int smem = kStages * kStageBytes + 256 + 1024;
   static bool attr = false;
   if (!attr) { NMX_CUDA(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }

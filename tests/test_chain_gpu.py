@@ -103,3 +103,22 @@ def test_full_size_properties():
     assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
     assert _rel_norm(g2, 2.0 * g1) < 1e-5
     assert _rel_norm(g1b, g1) < 1e-5
+
+
+def test_cta_pair_two_tile_chain_matches_one_tile_chain():
+    """nmx_chain2.cu (tcgen05 cta_group::2, two pair tiles in ping-pong, per-ray view-dir term in the dir layer's
+    epilogue; opt-in with NMX_ENABLE_CHAIN2=1) gives the one-tile chain's raw outputs up to the re-ordered view-dir
+    sum: 2 / 37 / 2368 / 8192 rays incl. ragged pair tiles.  Runs in a subprocess because the switch is read once."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NMX_ENABLE_CHAIN2="1")
+    env.pop("NMX_CHAIN2_DBG", None)
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "chain2_check.py")], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    errs = [float(x) for x in re.findall(r"rel max err ([0-9.e+-]+)", r.stdout)]
+    assert len(errs) == 4 and all(e < 2e-3 for e in errs), r.stdout
+    assert r.stdout.count("finite=True") == 4
