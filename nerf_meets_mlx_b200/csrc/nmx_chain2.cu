@@ -154,7 +154,15 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           const uint32_t bytes = (uint32_t)half_rows * 128u;
           for (int t = 0; t < (valid_y ? 2 : 1); ++t) {
             for (int s = 0; s < layer_slabs(l); ++s) {
-              mbar_wait(&empty[stage], phase ^ 1);
+              if (prm.dbg & 256) {  // experiment: non-suspending poll
+                uint32_t ok;
+                do {
+                  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                               : "=r"(ok) : "r"(smem_u32(&empty[stage])), "r"(phase ^ 1) : "memory");
+                } while (!ok);
+              } else {
+                mbar_wait(&empty[stage], phase ^ 1);
+              }
               if (prm.dbg & 4) {  // experiment: no weight traffic (results are garbage)
                 if (leader_cta) mbar_arrive(&full[stage]);
               } else if (prm.dbg & 16) {  // experiment: only the leader loads its half (results are garbage)
@@ -324,6 +332,17 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           mbar_wait(&tfull[t], lc[t] & 1u);
           tc_fence_after();
           uint32_t r[16];
+          if (prm.dbg & 512) {  // experiment: barrier traffic only (no TMEM loads, no proxy fences)
+            for (int st = 0; st < nsteps; ++st) {
+              __syncwarp();
+              if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + st]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[t]);
+            ++lc[t];
+            continue;
+          }
           tmem_ld_32x16(tacc + (uint32_t)(part * 16), r);
 #pragma unroll 1
           for (int st = 0; st < nsteps; ++st) {
