@@ -176,6 +176,10 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               } else if (prm.dbg & 32) {  // experiment: only CTA 1 loads its half
                 if (leader_cta) mbar_arrive_expect_tx(&full[stage], bytes);
                 else tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64, half_rows);
+              } else if (prm.dbg & 1024) {  // experiment: ONE tensor map for every layer (descriptor-cache test)
+                if (leader_cta) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
+                tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l == kNL - 1 ? kNL - 1 : 1], &full[stage],
+                                 (s & 3) * 64, (int)rank * half_rows);
               } else {
                 if (leader_cta) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
                 tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64,
@@ -207,7 +211,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           const int ns = layer_slabs(l);
           for (int t = 0; t < (valid_y ? 2 : 1); ++t) {
             mbar_wait(&tempty[t], (lc[t] & 1u) ^ 1u);  // the previous layer's epilogue has drained this accumulator
-            mbar_wait(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
+            if (!(prm.dbg & 4096)) mbar_wait(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             for (int s = 0; s < ns; ++s) {
@@ -216,7 +220,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               if (src == 4) mbar_wait(&pos_full[t], tc[t] & 1u);
               else {
                 mbar_wait(&act_ready[t * 4 + src], (gen[t] - 1u) & 1u);
-                mbar_wait(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
+                if (!(prm.dbg & 4096)) mbar_wait(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
               }
               tc_fence_after();
               const uint32_t a16 = smem16 + (uint32_t)((t * 5 + src) * (kChunk >> 4));
@@ -242,7 +246,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
         }
       }
     }
-    if (!leader_cta) {
+    if (!leader_cta && !(prm.dbg & 4096)) {
       // ---- CTA 1: this warp relays the local epilogue barriers to the leader, ONE remote arrival per barrier phase
       // (sixteen warps arriving remotely with cluster-scope release semantics each was measurably slow)
       const uint32_t tempty_peer_leader = mapa_u32(smem_u32(&tempty_peer[0]), 0);
@@ -257,13 +261,13 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
             if (l < kNL - 1) {
               for (int c = 0; c < 4; ++c) {
                 mbar_wait(&act_ready[t * 4 + c], gen[t] & 1u);
-                if (lane == 0) mbar_arrive_cluster(act_peer_leader + (uint32_t)(t * 4 + c) * 8u);
+                if (lane == 0) mbar_arrive_cluster_relaxed(act_peer_leader + (uint32_t)(t * 4 + c) * 8u);
                 __syncwarp();
               }
               ++gen[t];
             }
             mbar_wait(&tempty[t], lc[t] & 1u);
-            if (lane == 0) mbar_arrive_cluster(tempty_peer_leader + (uint32_t)t * 8u);
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_peer_leader + (uint32_t)t * 8u);
             __syncwarp();
             ++lc[t];
           }
@@ -329,7 +333,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
             const long long rr = row < prm.P ? row : (long long)prm.P - 1;
             dbias = prm.dir_bias + ((prm.p0 + rr) / prm.n_per_ray - prm.b0) * 128;
           }
-          mbar_wait(&tfull[t], lc[t] & 1u);
+          if (!(prm.dbg & 2048)) mbar_wait(&tfull[t], lc[t] & 1u);  // 2048: experiment, no tfull polling (garbage results)
           tc_fence_after();
           uint32_t r[16];
           if (prm.dbg & 512) {  // experiment: barrier traffic only (no TMEM loads, no proxy fences)

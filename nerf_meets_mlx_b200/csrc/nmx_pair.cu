@@ -28,6 +28,7 @@ struct PairArgs {
   int M, K;
   float* D;
   int ldd;
+  int b_only;    // experiment (NMX_PAIR_BONLY): only the weight halves are streamed (A stays whatever is in smem)
   int no_store;  // experiment (NMX_PAIR_NOSTORE): skip the fp32 output stores to time the TMA + MMA pipeline alone
 };
 
@@ -76,8 +77,12 @@ pair_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes;
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);  // both CTAs' A rows + B halves
-          tma_load_2d_pair(sA, &tmA, &full[stage], kb * 64, row0);
+          if (args.b_only) {
+            if (leader) mbar_arrive_expect_tx(&full[stage], kStageBytes);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * kStageBytes);  // both CTAs' A rows + B halves
+            tma_load_2d_pair(sA, &tmA, &full[stage], kb * 64, row0);
+          }
           tma_load_2d_pair(sA + 16384, &tmB, &full[stage], kb * 64, (int)rank * 128);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -153,6 +158,7 @@ extern "C" int nmx_gemm_pair_bf16(const void* A, const void* Bm, float* D, int64
   PairArgs a;
   a.M = (int)M; a.K = K; a.D = D; a.ldd = 256;
   a.no_store = getenv("NMX_PAIR_NOSTORE") ? 1 : 0;
+  a.b_only = getenv("NMX_PAIR_BONLY") ? 1 : 0;
   const int smem = kStages * kStageBytes + 256 + 1024;
   static bool attr = false;
   if (!attr) { NMX_CUDA(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }

@@ -200,6 +200,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// relaxed variant: no cluster-scope release fence.  A release at cluster scope waits for the SM's outstanding memory
+// traffic -- including bulk-async (TMA) loads in flight -- which cost ~1000 clocks per arrival in the CTA-pair chain.
+// Use only where the data hand-off is already ordered (writers fenced to the async proxy and a local barrier acquired).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS)
