@@ -865,12 +865,11 @@ int backward_chain(const Ctx& c, int64_t row0, int64_t P, int64_t cap, const flo
   return launch_chain_bwd(maps, prm, st);
 }
 
-// Inference of the reference's 8 x 256 view-dir net straight from rays: CTA pairs, two tiles in ping-pong (nmx_chain2.cu).
-// EXPERIMENTAL, opt-in with NMX_ENABLE_CHAIN2=1: numerically validated (tests/test_chain_gpu.py) but on B200 it is
-// still slower than the one-tile chain (1.89 ms vs 1.72 ms for 8192 x 192 points; DESIGN.md 3.1 has the breakdown).
+// Inference of the reference's 8 x 256 view-dir net straight from rays: CTA pairs, two tiles in ping-pong (nmx_chain2.cu);
+// NMX_DISABLE_CHAIN2=1 falls back to the one-tile chain.
 bool chain2_ok(const nmx_mlp_plan* p, int enc_kind, int n) {
   static int off = -1;
-  if (off < 0) off = getenv("NMX_ENABLE_CHAIN2") ? 0 : 1;
+  if (off < 0) off = getenv("NMX_DISABLE_CHAIN2") ? 1 : 0;
   return !off && chain_eligible(p) && p->cfg.use_viewdirs && p->W == 256 && p->D == 8 && p->cfg.skip_layer == 4 &&
          p->pos_pad == 64 && p->dir_pad == 64 && enc_fused_ok(p, enc_kind) && n >= 8;
 }

@@ -1,7 +1,7 @@
-"""chain2 (CTA pairs, two tiles in ping-pong; opt-in: NMX_ENABLE_CHAIN2=1) vs the one-tile-per-CTA chain: the inference
+"""chain2 (CTA pairs, two tiles in ping-pong; NMX_DISABLE_CHAIN2=1 turns it off) vs the one-tile-per-CTA chain: the inference
 forward (chain2 when enabled) against the training forward (always the one-tile chain) on the same inputs, and timing.
 
-    NMX_ENABLE_CHAIN2=1 python scripts/chain2_check.py      # NMX_CHAIN2_DBG selects the timing-only experiments
+    python scripts/chain2_check.py      # NMX_CHAIN2_DBG selects the timing-only experiments
 """
 import sys, time
 import torch

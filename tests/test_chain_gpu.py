@@ -79,7 +79,7 @@ def test_relu_sign_bits_match_saved_activations():
 
 
 def test_full_size_properties():
-    """BASELINE size (8192 x 192): training and inference forwards agree bit for bit, the backward is linear in d_out
+    """BASELINE size (8192 x 192): training and inference forwards agree (2e-3: different kernels), the backward is linear in d_out
     (bwd(2 d) == 2 bwd(d) exactly: powers of two commute with every rounding), and repeated runs are deterministic
     up to the fp32 atomic order of the weight-gradient reduction."""
     from nerf_meets_mlx_b200.models import NeRF
@@ -94,7 +94,9 @@ def test_full_size_properties():
     raw_t = net._fwd_raw(1, rays, z, None, B, n, save=True).clone()
     raw_i = net._fwd_raw(1, rays, z, None, B, n, save=False)
     assert torch.isfinite(raw_t).all()
-    assert torch.equal(raw_t, raw_i)
+    # inference runs on CTA pairs (nmx_chain2.cu): same arithmetic except that the per-ray view-dir term of the dir layer
+    # is summed separately (fp32) instead of inside the tensor-core accumulation
+    assert float((raw_t - raw_i).abs().max() / raw_t.abs().max()) < 2e-3
     net._fwd_raw(1, rays, z, None, B, n, save=True)
     d_raw = torch.randn(B * n, 4, device="cuda") * 1e-3
     g1 = net._bwd_raw(d_raw, B * n).clone()
@@ -107,15 +109,16 @@ def test_full_size_properties():
 
 def test_cta_pair_two_tile_chain_matches_one_tile_chain():
     """nmx_chain2.cu (tcgen05 cta_group::2, two pair tiles in ping-pong, per-ray view-dir term in the dir layer's
-    epilogue; opt-in with NMX_ENABLE_CHAIN2=1) gives the one-tile chain's raw outputs up to the re-ordered view-dir
-    sum: 2 / 37 / 2368 / 8192 rays incl. ragged pair tiles.  Runs in a subprocess because the switch is read once."""
+    epilogue) gives the one-tile chain's raw outputs up to the re-ordered view-dir sum: 2 / 37 / 2368 / 8192 rays incl.
+    ragged pair tiles (the script compares the inference forward = chain2 with the training forward = one-tile chain)."""
     import os
     import re
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, NMX_ENABLE_CHAIN2="1")
+    env = dict(os.environ)
     env.pop("NMX_CHAIN2_DBG", None)
+    env.pop("NMX_DISABLE_CHAIN2", None)
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "chain2_check.py")], cwd=root, env=env,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
