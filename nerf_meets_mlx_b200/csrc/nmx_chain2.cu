@@ -25,7 +25,8 @@
 //   tfull[t]  each     multicast commit after the last slab of a layer of slot t
 //   tempty[t] each     16 local arrivals: every epilogue warp of the CTA has read slot t's accumulator; CTA 1's otherwise
 //                      idle MMA warp relays its completion to the leader's tempty_peer[t] with ONE remote arrival
-//   act[t][c] each     16 local arrivals: chunk c of slot t's next-layer input is in shared memory; relayed likewise
+//   act[t][c] each     8 local arrivals (the warps that own chunk c): slot t's next-layer input chunk is in shared memory;
+//                      relayed likewise
 //                      (act_peer[t][c]); the leader's MMA warp waits for its local and the peer barrier
 //   posf[t]   leader   2 arrivals: both CTAs' encoder warps have written slot t's PE(pos) chunk
 //   pose[t]   each     multicast commit after the skip layer (last reader of the PE(pos) chunk)
@@ -123,7 +124,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
       mbar_init(&tempty[t], kEpiWarps);
       mbar_init(&tempty_peer[t], 1);
       for (int c = 0; c < 4; ++c) {
-        mbar_init(&act_ready[t * 4 + c], kEpiWarps);
+        mbar_init(&act_ready[t * 4 + c], kEpiWarps / 2);
         mbar_init(&act_peer[t * 4 + c], 1);
       }
       mbar_init(&pos_full[t], 2);
@@ -335,11 +336,10 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           }
           if (!(prm.dbg & 2048)) mbar_wait(&tfull[t], lc[t] & 1u);  // 2048: experiment, no tfull polling (garbage results)
           tc_fence_after();
-          uint32_t r[16];
           if (prm.dbg & 512) {  // experiment: barrier traffic only (no TMEM loads, no proxy fences)
-            for (int st = 0; st < nsteps; ++st) {
+            for (int h = 0; h < nsteps / 2; ++h) {
               __syncwarp();
-              if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + st]);
+              if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + 2 * h + (part >> 1)]);
             }
             tc_fence_before();
             __syncwarp();
@@ -347,33 +347,46 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
             ++lc[t];
             continue;
           }
-          tmem_ld_32x16(tacc + (uint32_t)(part * 16), r);
+          // Half steps: chunks (0, 1) then (2, 3); every warp takes 32 columns of one chunk per step.  With two tiles in
+          // flight the time to the FIRST chunk no longer matters (the other tile's MMAs cover it); the total does, and
+          // two 32-column steps cost less than four 16-column steps (fewer fence / barrier round trips per warp).
+          const int nh = nsteps / 2;
+          const int sub = part & 1;
+          uint32_t r32[32];
+          tmem_ld_32x32(tacc + (uint32_t)((part >> 1) * 64 + sub * 32), r32);
 #pragma unroll 1
-          for (int st = 0; st < nsteps; ++st) {
-            const int c0 = st * 64 + part * 16;
-            tmem_ld_wait_regs<16>(r);
+          for (int h = 0; h < nh; ++h) {
+            const int c = 2 * h + (part >> 1);
+            const int c0 = c * 64 + sub * 32;
+            tmem_ld_wait_regs<32>(r32);
+            if (h == nh - 1) {
+              // the accumulator is now completely in registers: hand it back before the math of the last chunks
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[t]);
+            }
             if (prm.dbg & 2) {
             } else if (l == kNL - 1) {  // per-ray view-dir term of the dir layer
 #pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
+              for (int i4 = 0; i4 < 8; ++i4) {
                 const float4 d = __ldg(reinterpret_cast<const float4*>(dbias + c0) + i4);
-                r[i4 * 4 + 0] = __float_as_uint(__uint_as_float(r[i4 * 4 + 0]) + d.x);
-                r[i4 * 4 + 1] = __float_as_uint(__uint_as_float(r[i4 * 4 + 1]) + d.y);
-                r[i4 * 4 + 2] = __float_as_uint(__uint_as_float(r[i4 * 4 + 2]) + d.z);
-                r[i4 * 4 + 3] = __float_as_uint(__uint_as_float(r[i4 * 4 + 3]) + d.w);
+                r32[i4 * 4 + 0] = __float_as_uint(__uint_as_float(r32[i4 * 4 + 0]) + d.x);
+                r32[i4 * 4 + 1] = __float_as_uint(__uint_as_float(r32[i4 * 4 + 1]) + d.y);
+                r32[i4 * 4 + 2] = __float_as_uint(__uint_as_float(r32[i4 * 4 + 2]) + d.z);
+                r32[i4 * 4 + 3] = __float_as_uint(__uint_as_float(r32[i4 * 4 + 3]) + d.w);
               }
-              epi_cols<true, 2, 2, false>(r, st, c0, 2 * part, 0, bias_addr, act_row_addr, swz, wrgb_addr, 0, hp, rgbp, 0u);
+              epi_cols<true, 2, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, wrgb_addr, 0, hp, rgbp, 0u);
             } else if (l == 7) {
-              epi_cols<true, 1, 2, false>(r, st, c0, 2 * part, 0, bias_addr, act_row_addr, swz, wa_addr, 1, hp, rgbp, 0u);
+              epi_cols<true, 1, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, wa_addr, 1, hp, rgbp, 0u);
             } else if (l == 8) {
-              epi_cols<false, 0, 2, false>(r, st, c0, 2 * part, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
+              epi_cols<false, 0, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
             } else {
-              epi_cols<true, 0, 2, false>(r, st, c0, 2 * part, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
+              epi_cols<true, 0, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
             }
-            if (st + 1 < nsteps) tmem_ld_32x16(tacc + (uint32_t)((st + 1) * 64 + part * 16), r);
+            if (h + 1 < nh) tmem_ld_32x32(tacc + (uint32_t)(c0 + 128), r32);
             fence_proxy_async_smem();
             __syncwarp();
-            if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + st]);
+            if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + c]);
           }
           if (l == 7) alpha_p[t] = hp[0];
           if (l == kNL - 1) {
@@ -395,9 +408,6 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // xchg is reused by the next tile's layers
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[t]);
           ++lc[t];
         }
       }

@@ -144,7 +144,8 @@ __device__ __forceinline__ void encode_pos_row(const float* __restrict__ rays, i
 // math + store of 32 columns [c0, c0 + 32) of chunk c held in r[] (fp32 accumulators of this thread's row)
 // NP4 = number of 8-column pieces (4: 32 columns, 2: 16 columns); piece0 = index of the first 16-byte piece inside the
 // chunk's 128-byte row; bit0 = first pair index of these columns inside their 32-column sign-bit word.
-template <bool RELU, int HEAD, int NP4, bool BITS>
+// FENCE: end with the generic->async proxy fence (callers that issue their next TMEM load first pass false)
+template <bool RELU, int HEAD, int NP4, bool BITS, bool FENCE = (NP4 == 4)>
 __device__ __forceinline__ void epi_cols(const uint32_t (&r)[8 * NP4], const int c, const int c0, const int piece0,
                                          const int bit0, const uint32_t bias_addr, const uint32_t act_row_addr,
                                          const uint32_t swz, const uint32_t hw_addr, const int head_n, float (&hp)[8],
@@ -204,7 +205,7 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[8 * NP4], const int
       asm volatile("st.shared.u8 [%0], %1;" ::"r"(bits_addr + 2u + (uint32_t)(bit0 >> 3)), "r"((bits >> (16 + bit0)) & 0xffu) : "memory");
     }
   }
-  if (NP4 == 4) fence_proxy_async_smem();  // quarter steps: the caller fences after issuing the next TMEM load
+  if (FENCE) fence_proxy_async_smem();
 }
 
 
