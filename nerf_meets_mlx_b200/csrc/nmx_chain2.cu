@@ -79,7 +79,11 @@ struct Chain2Params {
   long long p0, b0; int n_per_ray;
   const float* dir_bias;     // [rays of this launch, 128] fp32
   const float* consts;       // 16 B aligned: bias [kNL][256], w_alpha [256], w_rgb [3][128] (chain2_consts_kernel)
-  int dbg;                   // experiments (NMX_CHAIN2_DBG): bit 0 = encoders skip their work, bit 1 = epilogue math skipped
+  // timing-only experiments (NMX_CHAIN2_DBG, results are garbage): 1 encoders skip their work, 2 epilogue math skipped,
+  // 4 no weight TMA, 16 / 32 only the leader / only CTA 1 loads weights, 64 both load with local completion, 128 both load
+  // the same half, 256 non-suspending poll of the ring's empty barriers, 512 epilogue = barrier traffic only, 1024 one
+  // tensor map for all layers, 4096 no barrier relay from CTA 1, 8192 no proxy fence
+  int dbg;
 };
 struct Chain2Maps { CUtensorMap w[kNL]; };
 
@@ -384,7 +388,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               epi_cols<true, 0, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
             }
             if (h + 1 < nh) tmem_ld_32x32(tacc + (uint32_t)(c0 + 128), r32);
-            fence_proxy_async_smem();
+            if (!(prm.dbg & 8192)) fence_proxy_async_smem();  // 8192: timing experiment without the proxy fence
             __syncwarp();
             if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + c]);
           }
