@@ -216,16 +216,16 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           const int ns = layer_slabs(l);
           for (int t = 0; t < (valid_y ? 2 : 1); ++t) {
             mbar_wait(&tempty[t], (lc[t] & 1u) ^ 1u);  // the previous layer's epilogue has drained this accumulator
-            if (!(prm.dbg & 4096)) mbar_wait(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
+            if (!(prm.dbg & 4096)) mbar_wait_cluster(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             for (int s = 0; s < ns; ++s) {
               const int src = slab_src(l, s);
               mbar_wait(&full[stage], phase);
-              if (src == 4) mbar_wait(&pos_full[t], tc[t] & 1u);
+              if (src == 4) mbar_wait_cluster(&pos_full[t], tc[t] & 1u);
               else {
                 mbar_wait(&act_ready[t * 4 + src], (gen[t] - 1u) & 1u);
-                if (!(prm.dbg & 4096)) mbar_wait(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
+                if (!(prm.dbg & 4096)) mbar_wait_cluster(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
               }
               tc_fence_after();
               const uint32_t a16 = smem16 + (uint32_t)((t * 5 + src) * (kChunk >> 4));

@@ -200,6 +200,19 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// wait with cluster-scope acquire: for barriers whose phase is completed by arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
 // relaxed variant: no cluster-scope release fence.  A release at cluster scope waits for the SM's outstanding memory
 // traffic -- including bulk-async (TMA) loads in flight -- which cost ~1000 clocks per arrival in the CTA-pair chain.
 // Use only where the data hand-off is already ordered (writers fenced to the async proxy and a local barrier acquired).
