@@ -925,13 +925,23 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   }
   int64_t cap = infer_cap(p);
   c.al = act_layout(p, cap, false);
+  if (chain2_ok(p, enc_kind, n)) {
+    // The CTA-pair chain keeps nothing per point in the workspace: a launch is only limited by the per-ray scratch
+    // (13 KB of constants + 512 B per ray in the dirpe_bytes region), so whole ray batches go in one launch.
+    const int64_t max_rays = (dirpe_bytes(p) - 16384) / 512 - 2;
+    int64_t cap2 = max_rays * n;
+    if (cap2 > (int64_t)1 << 30) cap2 = (int64_t)1 << 30;
+    cap2 -= cap2 % 256;
+    for (int64_t p0 = 0; p0 < P; p0 += cap2) {
+      const int64_t npts = P - p0 < cap2 ? P - p0 : cap2;
+      EncIn ei{x_or_rays, ray_stride, z, p0, n};
+      if ((rc = forward_chain2(c, npts, out + p0 * out_cols, ei))) return rc;
+    }
+    return 0;
+  }
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t npts = P - p0 < cap ? P - p0 : cap;
     EncIn ei{x_or_rays, ray_stride, z, p0, n};
-    if (chain2_ok(p, enc_kind, n)) {
-      if ((rc = forward_chain2(c, npts, out + p0 * out_cols, ei))) return rc;
-      continue;
-    }
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, p0, npts, n))) return rc;
     if (chain_eligible(p)) rc = forward_chain(c, npts, cap, out + p0 * out_cols, out_cols, &ei);
     else rc = forward_chunk(c, npts, out + p0 * out_cols, out_cols);
