@@ -439,31 +439,32 @@ __global__ void chain2_consts_kernel(const float* __restrict__ params, Chain2Par
   }
 }
 
-// per-ray view-dir term of the dir layer: out[b, o] = sum_k bf16(W_dir[o, W + k]) * bf16(PE(dir_b)[k])  (fp32 accumulate)
+// per-ray view-dir term of the dir layer: out[b, o] = sum_k bf16(W_dir[o, W + k]) * bf16(PE(dir_b)[k])  (fp32 accumulate,
+// increasing k).  A block keeps the 27 x 128 bf16-rounded weight columns in shared memory and walks over rays.
 __global__ void __launch_bounds__(128)
 dir_bias_kernel(const float* __restrict__ rays, int ray_stride, long long b0, long long B, int n_freqs_dir,
                 const float* __restrict__ Wd, int ldw, int w_col0, float* __restrict__ out) {
-  __shared__ float pe[64];
-  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
-    const float* d = rays + (b0 + b) * ray_stride + (ray_stride - 3);
-    const int in_dir = 3 + 6 * n_freqs_dir;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      const int c = threadIdx.x;
-      float v = 0.0f;
-      if (c < 3) v = d[c];
-      else if (c < in_dir) {
-        const int qq = c - 3, k = qq / 6, rr = qq - 6 * k, fn = rr / 3, dd = rr - 3 * fn;
+  __shared__ float w_s[64 * 128];
+  __shared__ float pe[2][64];
+  const int in_dir = 3 + 6 * n_freqs_dir;
+  const int o = threadIdx.x;
+  for (int k = 0; k < in_dir; ++k) w_s[k * 128 + o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldw + w_col0 + k]));
+  int buf = 0;
+  for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+    if (o < in_dir) {
+      const float* d = rays + (b0 + b) * ray_stride + (ray_stride - 3);
+      float v;
+      if (o < 3) v = d[o];
+      else {
+        const int qq = o - 3, k = qq / 6, rr = qq - 6 * k, fn = rr / 3, dd = rr - 3 * fn;
         const float a = __fmul_rn(d[dd], (float)(k * k));
         v = fn ? cosf(a) : sinf(a);
       }
-      pe[c] = __bfloat162float(__float2bfloat16_rn(v));
+      pe[buf][o] = __bfloat162float(__float2bfloat16_rn(v));
     }
-    __syncthreads();
-    const int o = threadIdx.x;
+    __syncthreads();  // (double-buffered pe: one barrier per ray)
     float acc = 0.0f;
-    for (int k = 0; k < in_dir; ++k)
-      acc += __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldw + w_col0 + k])) * pe[k];
+    for (int k = 0; k < in_dir; ++k) acc += w_s[k * 128 + o] * pe[buf][k];
     out[b * 128 + o] = acc;
   }
 }
@@ -496,7 +497,7 @@ int launch_chain2(const Chain2Launch& a, cudaStream_t stream) {
   NMX_LAUNCH_CHECK();
   const long long b1 = (a.p0 + a.P - 1) / a.n_per_ray;
   const long long n_rays = b1 - prm.b0 + 1;
-  dir_bias_kernel<<<(unsigned)(n_rays < 65535 ? n_rays : 65535), 128, 0, stream>>>(
+  dir_bias_kernel<<<(unsigned)(n_rays < kNumSMs * 8 ? n_rays : kNumSMs * 8), 128, 0, stream>>>(
       a.rays, a.ray_stride, prm.b0, n_rays, a.n_freqs_dir, a.params + a.dir_w_off, a.dir_ldw, 256, dir_bias);
   NMX_LAUNCH_CHECK();
   static bool attr = false;
