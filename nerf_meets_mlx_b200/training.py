@@ -71,13 +71,18 @@ class NeRFTrainer:
             g.mul_(1.0 / self.world)
 
     # ------------------------------------------------------------------ one optimiser step on one net
-    def _step(self, model, rays, z, target, white_bkgd, g_buf):
+    def _grad(self, model, rays, z, target, white_bkgd, g_buf):
+        """Forward + backward of one net on this rank's rays: local gradient into g_buf, loss and compositing weights."""
         B, n = z.shape
         raw = model._fwd_raw(1, rays, z, None, B, n, save=True)
         rgb, _, _, weights, _ = ops.composite_fwd(raw.view(B, n, 4), z, rays[:, 3:6].contiguous(), white_bkgd=white_bkgd)
         loss, d_rgb = ops.mse_fwd_bwd(rgb, target)
         d_raw = ops.composite_bwd(raw.view(B, n, 4), z, rays[:, 3:6].contiguous(), d_rgb, white_bkgd=white_bkgd)
         model._bwd_raw(d_raw.view(B * n, 4), B * n, out=g_buf)
+        return loss, weights
+
+    def _step(self, model, rays, z, target, white_bkgd, g_buf):
+        loss, weights = self._grad(model, rays, z, target, white_bkgd, g_buf)
         self._allreduce_mean(g_buf)
         self.optimizer.update(model, g_buf, lr_dev=self._lr_dev)
         return loss, weights
@@ -86,6 +91,8 @@ class NeRFTrainer:
         """One pass of the reference loop body on this rank's shard of rays.  Returns device scalars."""
         if self.use_cuda_graph and self.world == 1:
             return self._train_iteration_graphed(rays_o, rays_d, target, u_vals)
+        if self.use_cuda_graph and u_vals is not None:
+            return self._train_iteration_graphed_dp(rays_o, rays_d, target, u_vals)
         self.iteration += 1
         out = self._iteration_body(rays_o, rays_d, target, u_vals)
         self._advance_lr()
@@ -131,6 +138,77 @@ class NeRFTrainer:
         self.iteration += 1
         self.optimizer.step_count += 2 if self.fine is not None else 1
         self._graph.replay()
+        self._advance_lr()
+        return io["out"]
+
+    def _train_iteration_graphed_dp(self, rays_o, rays_d, target, u_vals):
+        """Data-parallel graph replay: the iteration is cut at its two gradient all-reduces into three CUDA graphs that
+        share one memory pool (coarse forward/backward | Adam + coarse re-forward + resampling + fine forward/backward |
+        Adam); the NCCL all-reduces run eagerly between the replays, so no collective is ever captured."""
+        from . import _lib_loader as L
+        if self._lr_dev is None:
+            self._lr_dev = torch.empty((), dtype=torch.float32, device=rays_o.device)
+        self._lr_dev.fill_(float(self.optimizer.learning_rate))
+        key = ("dp", tuple(rays_o.shape))
+        if self._graph is None or self._graph_io["key"] != key:
+            if self.iteration == 0:  # first iteration eagerly: warm-up of the kernels and of the NCCL communicator
+                self.iteration += 1
+                out = self._iteration_body(rays_o, rays_d, target, u_vals)
+                self._advance_lr()
+                return out
+            io = {"key": key, "o": rays_o.clone(), "d": rays_d.clone(), "t": target.clone(), "u": u_vals.clone()}
+            inv_world = 1.0 / self.world
+            st = {}
+
+            def seg_a():
+                rays = assemble_rays(io["o"], io["d"], self.near, self.far)
+                z = ops.sample_z(rays[:, 6], rays[:, 7], self.n_samples, lindisp=bool(getattr(self.args, "lindisp", False)))
+                loss_c, weights = self._grad(self.coarse, rays, z, io["t"], self.white_bkgd, self._g_coarse)
+                st.update(rays=rays, z=z, weights=weights, out={"loss_coarse": loss_c})
+
+            def seg_b():
+                self._g_coarse.mul_(inv_world)
+                self.optimizer.update(self.coarse, self._g_coarse, lr_dev=self._lr_dev)
+                if self.fine is None:
+                    return
+                rays, z, weights = st["rays"], st["z"], st["weights"]
+                B = rays.shape[0]
+                if not self.reuse_coarse_forward:
+                    raw = self.coarse._fwd_raw(1, rays, z, None, B, self.n_samples, save=False)
+                    _, _, _, weights, _ = ops.composite_fwd(raw.view(B, self.n_samples, 4), z, rays[:, 3:6].contiguous(),
+                                                            white_bkgd=self.white_bkgd)
+                z_fine = ops.sample_pdf(z, weights, io["u"], want_imp=False)["z_merged"]
+                loss_f, _ = self._grad(self.fine, rays, z_fine, io["t"], False, self._g_fine)
+                st["out"]["loss_fine"] = loss_f
+                st["out"]["z_fine"] = z_fine
+
+            def seg_c():
+                self._g_fine.mul_(inv_world)
+                self.optimizer.update(self.fine, self._g_fine, lr_dev=self._lr_dev)
+
+            segs = [seg_a, seg_b] + ([seg_c] if self.fine is not None else [])
+            torch.cuda.synchronize()
+            pool = torch.cuda.graph_pool_handle()
+            graphs = []
+            n0 = L.launch_count()
+            for seg in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg()
+                graphs.append(g)
+            self.graph_launches = L.launch_count() - n0
+            io["out"], io["state"] = st["out"], st  # keeps the tensors handed from one graph to the next alive
+            self._graph, self._graph_io = graphs, io
+        io = self._graph_io
+        io["o"].copy_(rays_o); io["d"].copy_(rays_d); io["t"].copy_(target); io["u"].copy_(u_vals)
+        self.iteration += 1
+        self.optimizer.step_count += 2 if self.fine is not None else 1
+        self._graph[0].replay()
+        dist.all_reduce(self._g_coarse, op=dist.ReduceOp.SUM, group=self.pg)
+        self._graph[1].replay()
+        if self.fine is not None:
+            dist.all_reduce(self._g_fine, op=dist.ReduceOp.SUM, group=self.pg)
+            self._graph[2].replay()
         self._advance_lr()
         return io["out"]
 
