@@ -11,7 +11,7 @@ KW = dict(n_layers=8, width_layers=256, channel_input=63, channel_input_views=27
           list_skip_connection_layers=[4], is_use_view_directions=True)
 torch.manual_seed(3)
 net = NeRF(device="cuda", n_freqs_pos=10, n_freqs_dir=4, **KW)
-for B, n in ((2, 128), (37, 64), (2368, 64), (8192, 192)):
+for B, n in ((2, 128), (9, 64), (37, 64), (75, 64), (2368, 64), (8192, 192)):  # 1, 3, 10, 19, 592, 6144 pair tiles
     o = torch.randn(B, 3, device="cuda")
     d = torch.nn.functional.normalize(torch.randn(B, 3, device="cuda"), dim=-1)
     rays = torch.cat([o, d, torch.full((B, 1), 2.0, device="cuda"), torch.full((B, 1), 6.0, device="cuda"), d], -1).contiguous()
