@@ -177,7 +177,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    B = RAYS_PER_GPU
+    B = args.rays_per_gpu if args.rays_per_gpu > 0 else RAYS_PER_GPU
     # the iteration is captured once into CUDA graphs and replayed (no launch gaps); data parallel: three graphs cut at the
     # two gradient all-reduces, which run eagerly between the replays
     tr = NeRFTrainer(default_args(N_importance=N_IMPORTANCE, n_depth_samples=N_SAMPLES), device=dev, max_rays=B,
@@ -372,6 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays-per-gpu", type=int, default=0, help="override the 8192 rays per GPU of the headline step")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the training iteration eagerly (no CUDA graph)")

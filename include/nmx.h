@@ -38,6 +38,8 @@ int64_t nmx_launch_count(void);
 /* uniform.sample_z (sampling/uniform.py:7-18) / linear_disparity.sample_z (linear_disparity.py:8-19).
  * near, far: [B]; z: [B, n].  t_i = fp32(i) * fp32(1/(n-1)); z = near*(1-t) + far*t (two-product form). */
 int nmx_sample_z_fwd(const float* near, const float* far, float* z, int64_t B, int n, int lindisp, void* stream);
+/* the same with near / far taken from columns 6 / 7 of the assembled ray rows [B, ray_stride] (render.py:105-106) */
+int nmx_sample_z_rays(const float* rays, int ray_stride, float* z, int64_t B, int n, int lindisp, void* stream);
 /* add_noise_z (sampling/__init__.py:10-31) with the uniform draw t_rand [B, n] explicit. */
 int nmx_add_noise_z_fwd(const float* z, const float* t_rand, float* z_out, int64_t B, int n, float strength, void* stream);
 /* pos = o + z*d (rendering/render.py:142): rays [B, ray_stride] (o at col 0, d at col 3), z [B, n] -> pos [B, n, 3] */
@@ -52,6 +54,11 @@ int nmx_ray_points_fwd(const float* rays, int ray_stride, const float* z, float*
 int nmx_gen_rays(const float* c2w, int c2w_ld, double fx, double fy, double cx, double cy, int H, int W,
                  const int32_t* pix, int64_t B, float near, float far, float* rays, int ray_stride,
                  const float* image, int img_ld, float* target, void* stream);
+
+/* Ray-batch assembly from explicit origins / directions [B, 3]: rays[b] = [o, d, near, far, d/||d||] ([B, 11]), the row
+ * the reference's loss functions build before render_rays (__test_nerf.py:57-82, 97-104). */
+int nmx_assemble_rays(const float* rays_o, const float* rays_d, int64_t B, float near, float far, float* rays,
+                      void* stream);
 
 /* ---------------------------------------------------------------- positional encodings (K2a/K2b) */
 /* Embedder.embed (models/embedding.py:35-71): [x, sin(f0 x), cos(f0 x), ...], f_k = k^2 (reference quirk).
@@ -117,6 +124,28 @@ int nmx_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
  * training iteration follow the reference's decaying schedule, __test_nerf.py:302-305) */
 int nmx_adam_step_lrdev(float* p, const float* g, float* m, float* v, int64_t count, const float* lr_dev, float b1,
                         float b2, float eps, void* stream);
+
+/* ---------------------------------------------------------------- data-parallel gradient exchange */
+/* Peer-mapped device memory (CUDA IPC, one process per GPU on one NVSwitch box).  nmx_p2p_alloc: cudaMalloc'd, zeroed
+ * block + its 64-byte IPC handle (exchange the handles with any host-side transport, e.g. torch.distributed
+ * all_gather_object); nmx_p2p_open maps a PEER's block into this process (peer access enabled lazily). */
+int nmx_p2p_alloc(int64_t bytes, void** ptr, void* handle64);
+int nmx_p2p_open(const void* handle64, void** ptr);
+int nmx_p2p_close(void* ptr);
+int nmx_p2p_free(void* ptr);
+/* size of one rank's flags block (zero-initialised, peer-mapped): ready[8], done[8], epoch, arrival counter, error */
+int nmx_p2p_flags_bytes(void);
+/* One kernel = gradient all-reduce (mean) over NVLink peer memory + the MLX-style Adam update of the local replica
+ * (the two optimiser steps of __test_nerf.py:128-145 under ray-sharded data parallelism).  grads[r] / flags[r]: HOST
+ * arrays of `world` device pointers -- rank r's gradient buffer [count] fp32 and flags block as mapped in THIS process
+ * (own allocation for r == rank).  Sums in rank order, so all ranks update bit-identically.  p, m, v: local replica.
+ * g_avg: optional local copy of the averaged gradient.  lr_dev: optional device learning rate (CUDA-graph replays).
+ * Entry and exit barriers across the ranks are inside the kernel (system-scope flags, device-side epoch): the call is
+ * stream-ordered, capturable in a CUDA graph, and the gradient buffer may be overwritten as soon as it completes.
+ * A rank that never arrives is reported in flags[18] (1 = entry, 2 = exit barrier timeout) instead of hanging. */
+int nmx_allreduce_adam(const void* const* grads, void* const* flags, int rank, int world, float* p, float* m, float* v,
+                       float* g_avg, int64_t count, float lr, const float* lr_dev, float b1, float b2, float eps,
+                       void* stream);
 
 /* ---------------------------------------------------------------- NeRF MLP (K3), tcgen05/TMEM/TMA */
 /* Opaque plan for one NeRF network (models/NeRF.py:160-243) in its reference geometry.
@@ -197,6 +226,12 @@ int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long long* out, v
 /* TMEM -> register read-rate probe (tcgen05.ld.32x32b.x16 / .x32): out[2*cta] = clocks, out[2*cta+1] = bytes read */
 int nmx_diag_tmem_ld_rate(int iters, int warps, int mode, int batch, int ctas, long long* out, void* stream);
 int nmx_chain_trace_read(long long* out, int n);
+/* HBM bandwidth probes (scripts/bw_probe.py -> profiles/r2_bw_probe.txt).  mode 0 cudaMemsetAsync, 1 st.global.v4 fill,
+ * 2 bulk-async 1-D stores from shared memory (64 KB tiles, one CTA per SM), 3 ld.global.v4 read, 4 ld/st copy
+ * (src -> buf), 5 TMA 2-D tensor stores in the fused MLP chain's own pattern ([rows, 256] bf16 written as 128 x 64
+ * boxes), 6 TMA 2-D tile loads (the weight-gradient kernels' read pattern).  bytes % 64 KiB == 0; depth = bulk groups
+ * in flight per CTA (modes 2, 5). */
+int nmx_diag_bw(int mode, void* buf, const void* src, int64_t bytes, int ctas, int depth, void* stream);
 /* byte offsets of the training workspace regions: out[12] = {activation base, x0, h0, h stride, feature, hd, g0, g stride,
  * ghd, relu sign bits, capacity (points), x0 columns}; region offsets are relative to the activation base. */
 int nmx_mlp_debug_layout(const nmx_mlp_plan* plan, int64_t* out, int n);

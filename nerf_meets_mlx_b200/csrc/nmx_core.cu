@@ -43,14 +43,14 @@ extern "C" int64_t nmx_launch_count(void) { return nmx::g_launches.load(); }
 // K1: depth sampling.  Explicit _rn intrinsics pin the reference's operation order (no FMA contraction):
 //   t = i*step (+0);  z = near*(1-t) + far*t             (sampling/uniform.py:13-16)
 //   z = 1/(1/(near*(1-t)) + 1/(far*t))                   (sampling/linear_disparity.py:14-17, as written)
-__global__ void sample_z_kernel(const float* __restrict__ near, const float* __restrict__ far,
+__global__ void sample_z_kernel(const float* __restrict__ near, const float* __restrict__ far, int64_t bound_stride,
                                 float* __restrict__ z, int64_t total, int n, float step, int lindisp) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = idx / n;
     int i = (int)(idx - b * n);
     float t = __fmul_rn((float)i, step);
-    float nr = near[b], fr = far[b];
+    float nr = near[b * bound_stride], fr = far[b * bound_stride];
     float a = __fmul_rn(nr, __fsub_rn(1.0f, t));
     float c = __fmul_rn(fr, t);
     float v;
@@ -69,7 +69,19 @@ extern "C" int nmx_sample_z_fwd(const float* near, const float* far, float* z, i
   if (B == 0) return 0;
   float step = (float)((1.0 - 0.0) / (double)(n - 1));
   int64_t total = B * n;
-  sample_z_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, z, total, n, step, lindisp);
+  sample_z_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(near, far, 1, z, total, n, step, lindisp);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// same, with near / far read straight from the assembled ray rows (columns 6 and 7 of [B, ray_stride], render.py:105-106)
+extern "C" int nmx_sample_z_rays(const float* rays, int ray_stride, float* z, int64_t B, int n, int lindisp, void* stream) {
+  NMX_CHECK_ARG(B >= 0 && n >= 2 && ray_stride >= 8, "B >= 0, n >= 2, ray_stride >= 8");
+  if (B == 0) return 0;
+  NMX_CHECK_ARG(rays && z, "rays, z non-null");
+  float step = (float)((1.0 - 0.0) / (double)(n - 1));
+  int64_t total = B * n;
+  sample_z_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rays + 6, rays + 7, ray_stride, z, total, n, step, lindisp);
   NMX_LAUNCH_CHECK();
   return 0;
 }
@@ -363,6 +375,33 @@ extern "C" int nmx_gen_rays(const float* c2w, int c2w_ld, double fx, double fy, 
   NMX_CHECK_ARG(c2w && rays, "c2w, rays non-null");
   gen_rays_kernel<<<grid_for(B, 256, 16), 256, 256 * (ray_stride + 3) * sizeof(float), (cudaStream_t)stream>>>(c2w, c2w_ld, fx, fy, cx, cy, W, pix, B, near, far,
                                                                       rays, ray_stride, image, img_ld, target);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- ray-batch assembly from explicit origins/directions
+// rays[b] = [o(3), d(3), near, far, d/||d||(3)]: the row mlx_mse_coarse / mlx_mse_fine build before render_rays
+// (__test_nerf.py:57-82, 97-104: viewdirs = d / ||d||, near / far columns), one thread per ray.
+__global__ void __launch_bounds__(256)
+assemble_rays_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t B, float near, float far,
+                     float* __restrict__ rays) {
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const float ox = o[3 * b], oy = o[3 * b + 1], oz = o[3 * b + 2];
+    const float dx = d[3 * b], dy = d[3 * b + 1], dz = d[3 * b + 2];
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float nrm = __fsqrt_rn(n2);
+    float* r = rays + 11 * b;
+    r[0] = ox; r[1] = oy; r[2] = oz; r[3] = dx; r[4] = dy; r[5] = dz; r[6] = near; r[7] = far;
+    r[8] = __fdiv_rn(dx, nrm); r[9] = __fdiv_rn(dy, nrm); r[10] = __fdiv_rn(dz, nrm);
+  }
+}
+
+extern "C" int nmx_assemble_rays(const float* rays_o, const float* rays_d, int64_t B, float near, float far, float* rays,
+                                 void* stream) {
+  NMX_CHECK_ARG(B >= 0, "B >= 0");
+  if (B == 0) return 0;
+  NMX_CHECK_ARG(rays_o && rays_d && rays, "rays_o, rays_d, rays non-null");
+  assemble_rays_kernel<<<grid_for(B, 256, 4), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, B, near, far, rays);
   NMX_LAUNCH_CHECK();
   return 0;
 }

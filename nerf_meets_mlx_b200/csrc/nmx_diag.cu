@@ -126,6 +126,105 @@ tmem_ld_rate_kernel(int iters, int mode, int batch, long long* out) {
   if (warp == 0) tmem_dealloc<512>(tmem_ptr);
 }
 
+
+// ---- HBM bandwidth probes (scripts/bw_probe.py -> profiles/r2_bw_probe.txt): what a write-only / read-only stream
+// reaches on this part, measured with the store patterns the product kernels use.
+// mode 1: vectorised st.global.v4 fill, grid-stride, full occupancy.
+__global__ void __launch_bounds__(256)
+bw_fill_v4_kernel(uint4* __restrict__ dst, int64_t n16) {
+  const uint4 v = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+// mode 3: read-only ld.global.v4 stream (xor-reduced so the loads stay alive)
+__global__ void __launch_bounds__(256)
+bw_read_v4_kernel(const uint4* __restrict__ src, int64_t n16, uint32_t* __restrict__ sink) {
+  uint32_t acc = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(src + i);
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x9E3779B9u) *sink = acc;
+}
+// mode 4: copy (ld.global.v4 -> st.global.v4)
+__global__ void __launch_bounds__(256)
+bw_copy_v4_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + i);
+}
+// mode 2: bulk-async stores only.  One CTA per SM; each CTA owns a 64 KB staging tile in shared memory and writes it to
+// consecutive 64 KB tiles of global memory as 4 x 16 KB cp.async.bulk.global.shared::cta copies per tile, `depth` bulk
+// groups in flight (the fused chain keeps 1 tile-layer in flight per CTA).
+template <int DEPTH>
+__global__ void __launch_bounds__(128, 1)
+bw_bulk_store_kernel(uint8_t* __restrict__ dst, int64_t n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bulk_store_1d(dst + t * 65536 + c * 16384, smem + c * 16384, 16384);
+      tma_store_commit();
+      tma_store_wait_read<DEPTH - 1>();
+    }
+    tma_store_wait<0>();
+  }
+}
+// mode 5: the fused chain's own store pattern: a [rows, 256] bf16 row-major tensor written as 128-row x 64-column
+// SW128 boxes (cp.async.bulk.tensor.2d), 4 boxes = one 64 KB tile-layer, one bulk group per tile-layer.
+template <int DEPTH>
+__global__ void __launch_bounds__(128, 1)
+bw_tensor_store_kernel(const __grid_constant__ CUtensorMap map, int64_t n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tma_store_2d(&map, smem + c * 16384, c * 64, (int)(t * 128));
+      tma_store_commit();
+      tma_store_wait_read<DEPTH - 1>();
+    }
+    tma_store_wait<0>();
+  }
+}
+// mode 6: TMA tile loads only (the wgrad kernels' read pattern): 128 x 64 bf16 boxes of a [rows, 256] tensor into a
+// 4-slot shared-memory ring
+__global__ void __launch_bounds__(128, 1)
+bw_tensor_load_kernel(const __grid_constant__ CUtensorMap map, int64_t n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar[2];
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map);
+    int64_t issued = 0, done = 0;
+    const int64_t mine = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t k) {
+      const int64_t t = blockIdx.x + k * gridDim.x;
+      const int slot = (int)(k & 1);
+      mbar_arrive_expect_tx(&bar[slot], 65536);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tma_load_2d(smem + slot * 65536 + c * 16384, &map, &bar[slot], c * 64, (int)(t * 128));
+    };
+    for (; issued < 2 && issued < mine; ++issued) issue(issued);
+    for (; done < mine; ++done) {
+      mbar_wait(&bar[done & 1], (uint32_t)((done >> 1) & 1));
+      if (issued < mine) { issue(issued); ++issued; }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int nmx_diag_tmem_ld_rate(int iters, int warps, int mode, int batch, int ctas, long long* out, void* stream) {
@@ -142,6 +241,52 @@ extern "C" int nmx_diag_mma_rate(int N, int iters, int n_slabs, int ctas, long l
   const int smem_bytes = 16384 + n_slabs * 32768 + 1024;
   NMX_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   mma_rate_kernel<<<ctas, 128, smem_bytes, (cudaStream_t)stream>>>(N, iters, n_slabs, mode, out);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// HBM bandwidth probes; `bytes` must be a multiple of 64 KB.  mode 0 cudaMemsetAsync, 1 st.global.v4 fill,
+// 2 bulk-async (TMA 1-D) stores from shared memory, 3 ld.global.v4 read, 4 ld/st copy (src -> buf), 5 TMA 2-D tensor
+// stores in the fused chain's pattern ([rows,256] bf16, 128x64 boxes), 6 TMA 2-D tile loads.  depth = bulk groups in flight.
+extern "C" int nmx_diag_bw(int mode, void* buf, const void* src, int64_t bytes, int ctas, int depth, void* stream) {
+  NMX_CHECK_ARG(buf && bytes > 0 && bytes % 65536 == 0 && ctas > 0 && depth >= 1 && depth <= 3, "buf non-null; bytes % 64 KiB == 0; 1 <= depth <= 3");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n16 = bytes / 16, n_tiles = bytes / 65536;
+  const int smem_bytes = 65536 + 1024;
+  if (mode == 0) {
+    NMX_CUDA(cudaMemsetAsync(buf, 0x3c, (size_t)bytes, s));
+    return 0;
+  } else if (mode == 1) {
+    bw_fill_v4_kernel<<<ctas, 256, 0, s>>>((uint4*)buf, n16);
+  } else if (mode == 3) {
+    bw_read_v4_kernel<<<ctas, 256, 0, s>>>((const uint4*)buf, n16, (uint32_t*)buf);
+  } else if (mode == 4) {
+    NMX_CHECK_ARG(src != nullptr, "copy needs src");
+    bw_copy_v4_kernel<<<ctas, 256, 0, s>>>((const uint4*)src, (uint4*)buf, n16);
+  } else if (mode == 2) {
+#define NMX_BS(D)                                                                                                  \
+  NMX_CUDA(cudaFuncSetAttribute(bw_bulk_store_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+  bw_bulk_store_kernel<D><<<ctas, 128, smem_bytes, s>>>((uint8_t*)buf, n_tiles)
+    if (depth == 1) { NMX_BS(1); } else if (depth == 2) { NMX_BS(2); } else { NMX_BS(3); }
+#undef NMX_BS
+  } else if (mode == 5 || mode == 6) {
+    CUtensorMap map;
+    int rc = make_tmap_bf16_2d(&map, buf, (uint64_t)(bytes / 512), 256, 256, 128);
+    if (rc) return rc;
+    if (mode == 6) {
+      NMX_CUDA(cudaFuncSetAttribute(bw_tensor_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 1024));
+      bw_tensor_load_kernel<<<ctas, 128, 2 * 65536 + 1024, s>>>(map, n_tiles);
+    } else {
+#define NMX_TS(D)                                                                                                    \
+  NMX_CUDA(cudaFuncSetAttribute(bw_tensor_store_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+  bw_tensor_store_kernel<D><<<ctas, 128, smem_bytes, s>>>(map, n_tiles)
+      if (depth == 1) { NMX_TS(1); } else if (depth == 2) { NMX_TS(2); } else { NMX_TS(3); }
+#undef NMX_TS
+    }
+  } else {
+    set_error("nmx_diag_bw: mode in [0,6]");
+    return NMX_E_BADARG;
+  }
   NMX_LAUNCH_CHECK();
   return 0;
 }

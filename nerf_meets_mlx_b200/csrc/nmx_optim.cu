@@ -1,6 +1,7 @@
 // K6: MSE loss (+ its gradient) and the Adam update of the reference's training step
 // (entrypoints/__test_nerf.py:88,124,128-145; models/NeRF.py:120).  Pure streaming kernels, float4 vectorised.
 #include "nmx_common.cuh"
+#include "nmx_optim.cuh"
 
 using namespace nmx;
 
@@ -35,12 +36,11 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   if (lr_dev != nullptr) lr = __ldg(lr_dev);  // learning rate from device memory (CUDA-graph replays)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i];
-    float mi = b1 * m[i] + (1.0f - b1) * gi;
-    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], lr, b1, b2, eps, c1, c2);
     m[i] = mi;
     v[i] = vi;
-    p[i] = p[i] - lr * (mi * c1) / (sqrtf(vi * c2) + eps);
+    p[i] = pi;
   }
 }
 

@@ -25,6 +25,12 @@ class _LinearView:
 
 
 class _MLPFunction(torch.autograd.Function):
+    """Autograd node of one MLP pass.  The activations a backward needs live in the model's ONE workspace; every saving
+    forward gets a generation id.  If a later saving forward on the same model has overwritten them by the time this
+    node's backward runs (chunked callers: run_model's netchunk loop, batchify_rays, render_rays_eval with
+    network_fine=None), the forward is RECOMPUTED from the node's own (small) inputs first -- never a silent gradient
+    from the wrong activations."""
+
     @staticmethod
     def forward(ctx, flat, model, enc_kind, x_or_rays, z, bands, B, n):
         # grad mode is off inside Function.forward; an already-encoded input (enc_kind 0) may itself need a gradient:
@@ -34,14 +40,24 @@ class _MLPFunction(torch.autograd.Function):
         out = model._fwd_raw(enc_kind, x_or_rays, z, bands, B, n, save=need_grad)
         ctx.model = model
         ctx.P = B * n
+        if need_grad:
+            ctx.gen = model._save_gen
+            ctx.save_for_backward(x_or_rays, z, bands)
+            ctx.args = (enc_kind, B, n)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
+        model = ctx.model
+        if ctx.gen != model._save_gen:  # a later forward reused the workspace: rebuild this pass's activations
+            model.recomputed_backwards += 1
+            x_or_rays, z, bands = ctx.saved_tensors
+            enc_kind, B, n = ctx.args
+            model._fwd_raw(enc_kind, x_or_rays.detach(), z, bands, B, n, save=True)
         if ctx.input_grad:
-            g, d_x = ctx.model._bwd_raw(d_out.contiguous(), ctx.P, want_input_grad=True)
+            g, d_x = model._bwd_raw(d_out.contiguous(), ctx.P, want_input_grad=True)
             return g, None, None, d_x, None, None, None, None
-        g = ctx.model._bwd_raw(d_out.contiguous(), ctx.P)
+        g = model._bwd_raw(d_out.contiguous(), ctx.P)
         return g, None, None, None, None, None, None, None
 
 
@@ -56,7 +72,7 @@ class NeRF(torch.nn.Module):
 
     def __init__(self, n_layers=8, width_layers=256, channel_input=3, channel_input_views=3, channel_output=4,
                  list_skip_connection_layers=[4], is_use_view_directions=False, device="cuda", seed=None,
-                 n_freqs_pos=0, n_freqs_dir=0, max_points=1 << 16):
+                 n_freqs_pos=0, n_freqs_dir=0, max_points=1 << 16, max_save_points=1 << 21):
         super().__init__()
         self.D = n_layers
         self.W = width_layers
@@ -80,7 +96,10 @@ class NeRF(torch.nn.Module):
         self._ws = None
         self._ws_train = False
         self._max_points = int(max_points)
+        self.max_save_points = int(max_save_points)  # largest differentiable pass kept in one workspace (~10 KB/point)
         self._packed_version = -1
+        self._save_gen = 0              # generation id of the activations currently held in the workspace
+        self.recomputed_backwards = 0   # backward passes that had to rebuild overwritten activations
         self.out_cols = 4 if self.is_use_view_directions else channel_output
 
     # ---------------------------------------------------------------- parameter tree
@@ -193,6 +212,8 @@ class NeRF(torch.nn.Module):
         stride = x_or_rays.shape[-1] if enc_kind == 1 else 0
         L.call("nmx_mlp_fwd", self._plan, L.ptr(self._ws), L.ptr(self.flat), L.i32(enc_kind), L.ptr(x_or_rays),
                L.i32(stride), L.ptr(z), L.ptr(bands), L.ptr(out), L.i64(B), L.i32(n), L.i32(1 if save else 0), L.stream())
+        if save:
+            self._save_gen += 1
         return out
 
     def _bwd_raw(self, d_out, P, out=None, want_input_grad=False):
@@ -221,7 +242,13 @@ class NeRF(torch.nn.Module):
         if x.shape[-1] != expect:
             raise ValueError(f"expected last dim {expect}, got {x.shape[-1]}")
         P = x.numel() // expect
-        out = _MLPFunction.apply(self.flat, self, 0, x.reshape(P, expect), None, None, P, 1)
+        x2 = x.reshape(P, expect)
+        rows = self.max_save_points
+        if torch.is_grad_enabled() and (self.flat.requires_grad or x2.requires_grad) and P > rows:
+            out = torch.cat([_MLPFunction.apply(self.flat, self, 0, x2[i:i + rows], None, None, min(rows, P - i), 1)
+                             for i in range(0, P, rows)], dim=0)
+        else:
+            out = _MLPFunction.apply(self.flat, self, 0, x2, None, None, P, 1)
         return out.reshape(*x.shape[:-1], self.out_cols)
 
     def forward_rays(self, rays, z_vals):
@@ -229,6 +256,13 @@ class NeRF(torch.nn.Module):
         rays = rays.float().contiguous()
         z_vals = z_vals.float().contiguous()
         B, n = z_vals.shape
+        rows = max(1, self.max_save_points // n)
+        if torch.is_grad_enabled() and self.flat.requires_grad and B > rows:
+            # a differentiable pass keeps ~10 KB of activations per point: bound the workspace by running ray chunks as
+            # separate autograd nodes (their backward recomputes what a later chunk overwrote)
+            outs = [_MLPFunction.apply(self.flat, self, 1, rays[i:i + rows], z_vals[i:i + rows], None, min(rows, B - i), n)
+                    for i in range(0, B, rows)]
+            return torch.cat(outs, dim=0).reshape(B, n, self.out_cols)
         out = _MLPFunction.apply(self.flat, self, 1, rays, z_vals, None, B, n)
         return out.reshape(B, n, self.out_cols)
 
@@ -280,15 +314,30 @@ class AdamMLX:
         self.state = {}
         self.step_count = 0
 
+    def moments(self, model, like):
+        """(m, v) of `model` -- ONE pair per parameter-tree shape when `shared_state` (the reference quirk)."""
+        key = ("shared", like.numel()) if self.shared_state else id(model)
+        if key not in self.state:
+            self.state[key] = (torch.zeros_like(like), torch.zeros_like(like))
+        return self.state[key]
+
+    def update_exchange(self, model, xchg, buf_idx, lr_dev=None):
+        """Data-parallel step: average gradient buffer `buf_idx` of the peer exchange over the ranks and update this
+        replica, one kernel (nmx_allreduce_adam).  No bias correction (MLX 0.7)."""
+        if self.bias_correction:
+            raise NotImplementedError("the fused exchange + Adam kernel implements the MLX-style update only")
+        m, v = self.moments(model, model.flat.data)
+        self.step_count += 1
+        xchg.allreduce_adam(buf_idx, model.flat.data, m, v, self.learning_rate, self.betas[0], self.betas[1], self.eps,
+                            lr_dev=lr_dev)
+        model.mark_params_updated()
+
     def update(self, model, grads=None, lr_dev=None):
         """`lr_dev`: optional device scalar holding the learning rate (used when the iteration is replayed from a CUDA
         graph, where a by-value learning rate would be frozen at capture time)."""
         from .. import ops
         g = grads if grads is not None else model.flat.grad
-        key = ("shared", g.numel()) if self.shared_state else id(model)
-        if key not in self.state:
-            self.state[key] = (torch.zeros_like(g), torch.zeros_like(g))
-        m, v = self.state[key]
+        m, v = self.moments(model, g)
         self.step_count += 1
         ops.adam_step(model.flat.data, g, m, v, self.learning_rate, self.betas[0], self.betas[1], self.eps,
                       self.bias_correction, self.step_count, lr_dev=lr_dev)

@@ -22,6 +22,16 @@ def sample_z(near, far, n_samples, lindisp=False):
     return z
 
 
+def sample_z_rays(rays, n_samples, lindisp=False):
+    """sample_z with near / far read from columns 6 / 7 of the assembled ray rows [B, >=8] (no column copies)."""
+    rays = _f32c(rays)
+    require_cuda(rays)
+    B = rays.shape[0]
+    z = torch.empty((B, n_samples), dtype=torch.float32, device=rays.device)
+    call("nmx_sample_z_rays", ptr(rays), i32(rays.shape[1]), ptr(z), i64(B), i32(n_samples), i32(1 if lindisp else 0), stream())
+    return z
+
+
 def add_noise_z(z_vals, t_rand, strength):
     z = _f32c(z_vals)
     require_cuda(z)
@@ -40,6 +50,28 @@ def ray_points(rays, z):
     pos = torch.empty((B, n, 3), dtype=torch.float32, device=z.device)
     call("nmx_ray_points_fwd", ptr(rays), i32(rays.shape[1]), ptr(z), ptr(pos), i64(B), i32(n), stream())
     return pos
+
+
+def assemble_rays(rays_o, rays_d, near, far):
+    """[o, d, near, far, d/||d||] rows [B, 11] from explicit origins / directions (__test_nerf.py:57-82)."""
+    o, d = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3)
+    require_cuda(o, d)
+    B = o.shape[0]
+    rays = torch.empty((B, 11), dtype=torch.float32, device=o.device)
+    call("nmx_assemble_rays", ptr(o), ptr(d), i64(B), f32(near), f32(far), ptr(rays), stream())
+    return rays
+
+
+def _rows3(t):
+    """A [B, >=3] fp32 CUDA matrix whose rows are contiguous (a column slice of the ray batch qualifies): the tensor
+    and its row stride, without copying."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    if not t.is_cuda:
+        raise NmxError("nerf_meets_mlx_b200 ops need CUDA tensors (no CPU fallback exists)")
+    return t, int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
 
 
 def gen_rays(H, W, K, c2w, pix=None, near=0.0, far=1.0, n_cols=11, image=None):
@@ -136,8 +168,9 @@ def hashgrid_bwd(x, scaled_res, d_out, L, F, log2_T):
 
 # ----------------------------------------------------------------------------------------- compositing
 def composite_fwd(raw, z, rays_d, noise=None, raw_noise_std=0.0, white_bkgd=False):
-    raw, z, rays_d = _f32c(raw), _f32c(z), _f32c(rays_d)
-    require_cuda(raw, z, rays_d)
+    raw, z = _f32c(raw), _f32c(z)
+    rays_d, d_stride = _rows3(rays_d)
+    require_cuda(raw, z)
     B, n = z.shape
     assert raw.shape == (B, n, 4), f"raw must be [B, n, 4], got {tuple(raw.shape)}"
     dev = z.device
@@ -147,20 +180,21 @@ def composite_fwd(raw, z, rays_d, noise=None, raw_noise_std=0.0, white_bkgd=Fals
     weights = torch.empty((B, n, 1), dtype=torch.float32, device=dev)
     depth = torch.empty((B, 1), dtype=torch.float32, device=dev)
     nz = _f32c(noise) if (noise is not None and raw_noise_std > 0) else None
-    call("nmx_composite_fwd", ptr(raw), ptr(z), ptr(rays_d), i32(rays_d.shape[-1]), ptr(nz), f32(raw_noise_std),
+    call("nmx_composite_fwd", ptr(raw), ptr(z), ptr(rays_d), i32(d_stride), ptr(nz), f32(raw_noise_std),
          i32(1 if white_bkgd else 0), ptr(rgb), ptr(disp), ptr(acc), ptr(weights), ptr(depth), i64(B), i32(n), stream())
     return rgb, disp, acc, weights, depth
 
 
 def composite_bwd(raw, z, rays_d, d_rgb, d_disp=None, d_acc=None, d_depth=None, d_weights=None, noise=None,
                   raw_noise_std=0.0, white_bkgd=False):
-    raw, z, rays_d, d_rgb = _f32c(raw), _f32c(z), _f32c(rays_d), _f32c(d_rgb)
-    require_cuda(raw, z, rays_d, d_rgb)
+    raw, z, d_rgb = _f32c(raw), _f32c(z), _f32c(d_rgb)
+    rays_d, d_stride = _rows3(rays_d)
+    require_cuda(raw, z, d_rgb)
     B, n = z.shape
     opt = [None if t is None else _f32c(t) for t in (d_disp, d_acc, d_depth, d_weights)]
     nz = _f32c(noise) if (noise is not None and raw_noise_std > 0) else None
     d_raw = torch.empty((B, n, 4), dtype=torch.float32, device=z.device)
-    call("nmx_composite_bwd", ptr(raw), ptr(z), ptr(rays_d), i32(rays_d.shape[-1]), ptr(nz), f32(raw_noise_std),
+    call("nmx_composite_bwd", ptr(raw), ptr(z), ptr(rays_d), i32(d_stride), ptr(nz), f32(raw_noise_std),
          i32(1 if white_bkgd else 0), ptr(d_rgb), ptr(opt[0]), ptr(opt[1]), ptr(opt[2]), ptr(opt[3]), ptr(d_raw),
          i64(B), i32(n), stream())
     return d_raw

@@ -171,11 +171,31 @@ def build_rays(H, W, K, c2w, near, far, use_viewdirs=False, ndc=False, c2w_stati
 
 
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, far=1.0, use_viewdirs=False,
-           c2w_staticcam=None, **kwargs):
-    """render (rendering/render.py:268-345) -> [rgb_map, disp_map, acc_map, extras_dict], each reshaped to [H, W, .]."""
+           c2w_staticcam=None, process_group=None, **kwargs):
+    """render (rendering/render.py:268-345) -> [rgb_map, disp_map, acc_map, extras_dict], each reshaped to [H, W, .].
+
+    `process_group` (not in the reference, which is single-device): shard the frame's [H*W, 11] ray buffer into one
+    contiguous ray tile per rank, render the local tile with the same chunk loop, and all_gather the
+    per-ray results, so every rank returns the same assembled frame as a single-GPU call -- rays are independent, so
+    the assembled frame is bit-identical to it.  No collective runs inside the chunk loop."""
     device = kwargs.pop("device", "cuda")
     rays_linear, rays_shape = build_rays(H, W, K, c2w, near, far, use_viewdirs, ndc, c2w_staticcam, rays, device)
-    results_batched = batchify_rays(rays_linear, chunk, **kwargs)
+    if process_group is None:
+        results_batched = batchify_rays(rays_linear, chunk, **kwargs)
+    else:
+        import torch.distributed as dist
+        from ..parallel import gather_tiles, ray_tile
+        n_rays = rays_linear.shape[0]
+        start, stop = ray_tile(n_rays, dist.get_rank(process_group), dist.get_world_size(process_group))
+        if kwargs.get("u_vals") is not None:
+            kwargs = dict(kwargs, u_vals=kwargs["u_vals"][start:stop])
+        if stop > start:
+            local = batchify_rays(rays_linear[start:stop], chunk, **kwargs)
+        else:  # more ranks than rays: an empty tile with the right keys / trailing shapes
+            if kwargs.get("u_vals") is not None:
+                kwargs = dict(kwargs, u_vals=None)
+            local = {k: v[:0] for k, v in batchify_rays(rays_linear[:1], chunk, **kwargs).items()}
+        results_batched = {k: gather_tiles(v.contiguous(), n_rays, process_group) for k, v in local.items()}
     for key, val in results_batched.items():
         results_batched[key] = val.reshape(tuple(list(rays_shape[:-1]) + list(val.shape[1:])))
     k_extract = ["rgb_map", "disp_map", "acc_map"]

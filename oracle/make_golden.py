@@ -10,6 +10,7 @@ NumPy-backed stand-in in oracle/mlx_shim (see its docstring for the assumed MLX 
 """
 import os
 import sys
+import types
 
 import numpy as np
 import torch
@@ -218,6 +219,74 @@ def main():
         g[f"sh_dim_{lv}"] = enc.get_out_dim()
     np.savez_compressed(os.path.join(OUT, "sh.npz"), **g)
 
+    # ---- MultiHashEncoding (encoding/multi_hash.py:13-137): the class cannot run as committed, its
+    # pieces can.  Everything below executes the reference's OWN source lines, read from the reference tree at
+    # generation time:
+    #   (1) the real constructor (:14-53) -> growing_factor, scaled_res (:32-40), hash_table_size (:43);
+    #   (2) `hash` (:61-77) on int64 coordinate arrays (int32 * 2654435761 has no defined result; on int64 nothing
+    #       overflows for |coord| < 2^31 and the low log2_T bits equal the uint32-wraparound result), incl. negatives;
+    #   (3) `__call__` (:79-137) with ONLY its eight table-lookup lines (:112-119, which call a Python list) replaced by
+    #       the canonical per-level lookup `tables[level, hash(int64(grid_k))]`: the scaling, ceil/floor, corner
+    #       construction (:90-109) and the interpolation + flatten (:121-137) are the reference's text, exec'd verbatim.
+    import inspect
+    import textwrap
+    from mlx_nerf.encoding import multi_hash as RMH
+    g = {}
+    rng_h = np.random.default_rng(20261019)  # own stream: the sections below keep their draws
+    for tag, (L_, nmin, nmax, F_, log2T) in {"a": (16, 16, 2048, 2, 19), "b": (8, 16, 512, 4, 14), "c": (1, 4, 4, 1, 10),
+                                             "d": (5, 3, 100, 2, 12)}.items():
+        mnn.seed(100 + L_)
+        enc = RMH.MultiHashEncoding(3, L_, nmin, nmax, F_, log2T)
+        g[f"{tag}_cfg"] = np.array([L_, nmin, nmax, F_, log2T], np.int64)
+        g[f"{tag}_growing_factor"] = np.asarray(enc.growing_factor, np.float32)
+        g[f"{tag}_scaled_res"] = np.asarray(enc.scaled_res, np.float32)
+        g[f"{tag}_table_size"] = np.int64(enc.hash_table_size)
+        g[f"{tag}_out_dim"] = np.int64(enc.get_out_dim())
+        assert len(enc.hash_table) == L_ and enc.hash_table[0].weight.shape == (2 ** log2T, F_)
+    # (2) hash on int64 arrays [B, L, 3]
+    coords = np.concatenate([
+        rng_h.integers(0, 2049, size=(4000, 4, 3)),                   # the C4 range
+        rng_h.integers(0, 2 ** 31 - 1, size=(500, 4, 3)),             # large non-negative
+        rng_h.integers(-2 ** 31, 0, size=(500, 4, 3)),                # negative (unclamped inputs)
+        np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], [[1, 1, 1], [2047, 2048, 2047], [-1, -1, -1], [5, -7, 9]]]),
+    ]).astype(np.int64)
+    g["hash_coords"] = coords
+    for log2T in (10, 14, 19, 24):
+        stub = types.SimpleNamespace(hash_table_size=2 ** log2T)
+        g[f"hash_T{log2T}"] = np.asarray(RMH.MultiHashEncoding.hash(stub, coords.copy()), np.int64)
+    # (3) __call__ with the lookup lines replaced
+    src = inspect.getsource(RMH.MultiHashEncoding.__call__).splitlines()
+    i_a = next(i for i, ln in enumerate(src) if "in_array_scaled = in_array[..., None, :]" in ln)
+    i_b = next(i for i, ln in enumerate(src) if "hashed_0 = self.hash_table(self.hash(grid_0))" in ln)
+    i_c = next(i for i, ln in enumerate(src) if "offset = in_array_scaled - in_sf" in ln)
+    assert all(f"hashed_{k} = self.hash_table(self.hash(grid_{k}))" in src[i_b + k] for k in range(8))
+    body = src[i_a:i_b] + [f"        hashed_{k} = lookup(self.hash(grid_{k}.astype('int64')))" for k in range(8)] + src[i_c:]
+    fn_src = "def _call(self, in_array, lookup, mx):\n" + textwrap.dedent("\n".join(body)).replace("\n", "\n    ")
+    fn_src = fn_src.replace("def _call(self, in_array, lookup, mx):\n", "def _call(self, in_array, lookup, mx):\n    ")
+    ns = {}
+    exec(compile(fn_src, "<multi_hash.__call__ :90-109,121-137>", "exec"), ns)
+    for tag, (L_, nmin, nmax, F_, log2T, B_, lo, hi) in {"a": (16, 16, 2048, 2, 19, 257, 0.0, 1.0),
+                                                          "b": (8, 16, 512, 4, 14, 64, -1.5, 2.5)}.items():
+        mnn.seed(200 + L_)
+        enc = RMH.MultiHashEncoding(3, L_, nmin, nmax, F_, log2T)
+        # tables are large (a: 64 MiB): drawn from their own seeded stream so that the tests can redraw them
+        tables = np.random.default_rng(900 + L_).uniform(-1.0, 1.0, size=(L_, 2 ** log2T, F_)).astype(np.float32)
+        x = rng_h.uniform(lo, hi, size=(B_, 3)).astype(np.float32)
+        x[0] = [0.0, 0.5, 1.0]          # exact-integer scaled coordinates: ceil == floor, offset 0
+        x[1] = [0.25, 0.125, 0.75]
+        lv = np.arange(L_)[None, :]
+        seen = []
+
+        def lookup(idx, tables=tables, lv=lv, seen=seen):
+            seen.append(np.asarray(idx, np.int64))
+            return tables[lv, np.asarray(idx, np.int64)]
+        out = ns["_call"](enc, x, lookup, mx)
+        g.update({f"call_{tag}_x": x, f"call_{tag}_out": np.asarray(out, np.float32),
+                  f"call_{tag}_idx": np.stack(seen, -1), f"call_{tag}_cfg": np.array([L_, nmin, nmax, F_, log2T], np.int64)})
+        g[f"call_{tag}_tables_sample"] = tables[:, :64].copy()
+        g[f"call_{tag}_tables_rng"] = np.int64(900 + L_)
+    np.savez_compressed(os.path.join(OUT, "hashgrid.npz"), **g)
+
     # ---- metrics (ops/metric.py:12-18)
     from mlx_nerf.ops import metric
     pa = rng.random(size=(9, 7, 3)).astype(np.float32)
@@ -228,7 +297,6 @@ def main():
     # ---- Blender loader (dataset/dataloader.py:20-113) on the tiny committed scene tests/golden/blender_tiny.
     # imageio / matplotlib are not in this image: imageio.v2.imread is stood in by PIL (same uint8 array), pyplot by
     # an empty module (only validate_dataset, a plotting helper, touches it).
-    import types
     from PIL import Image
     scene = os.path.join(OUT, "blender_tiny")
     make_tiny_scene(scene, np.random.default_rng(5))

@@ -17,10 +17,11 @@ gpu = "gpu"
 
 
 def _c(x):
+    keep = isinstance(x, mxarray)  # MLX-promotion arrays (see `mxarray`) stay what they are
     x = _np.asarray(x)
     if x.dtype == _np.float64:
-        return x.astype(_np.float32)
-    return x
+        x = x.astype(_np.float32)
+    return x.view(mxarray) if keep else x
 
 
 def array(x, dtype=None):
@@ -54,13 +55,31 @@ def linspace(start, stop, num=50, dtype=float32):
     return (seq * step + _np.float32(start)).astype(dtype)
 
 
+class mxarray(_np.ndarray):
+    """ndarray with MLX's type promotion in ufuncs: an integer array meeting a floating array (or scalar) is
+    promoted to float32 (NumPy would go to float64), and float64 never appears.  Returned by `arange` only (its one
+    caller on the path is MultiHashEncoding.__init__, multi_hash.py:32-40: `growing_factor ** levels`)."""
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        arrs = [(_np.asarray(x) if isinstance(x, _np.ndarray) else x) for x in inputs]
+        has_float = any((isinstance(a, float) or (isinstance(a, _np.ndarray) and a.dtype.kind == "f")) for a in arrs)
+        if has_float:
+            arrs = [a.astype(_np.float32) if isinstance(a, _np.ndarray) and a.dtype != _np.float32 else a for a in arrs]
+        r = getattr(ufunc, method)(*arrs, **kwargs)
+        if isinstance(r, _np.ndarray):
+            if r.dtype == _np.float64:
+                r = r.astype(_np.float32)
+            return r.view(mxarray)
+        return r
+
+
 def arange(*a, dtype=None):
     r = _np.arange(*a)
     if dtype is not None:
-        return r.astype(dtype)
+        return r.astype(dtype).view(mxarray)
     if r.dtype == _np.int64:
-        return r.astype(_np.int32)
-    return _c(r)
+        return r.astype(_np.int32).view(mxarray)
+    return _c(r).view(mxarray)
 
 
 def concatenate(arrs, axis=0):

@@ -81,3 +81,17 @@ init = _Init()
 
 def value_and_grad(model, fn):
     raise NotImplementedError("autodiff is not part of the shim; gradients are pinned by torch autograd in oracle/")
+
+
+class _Init:
+    """nn.init.uniform(low, high) -> initialiser returning a NEW array (MLX initialisers are functional; the reference
+    discards the result at multi_hash.py:51)."""
+
+    @staticmethod
+    def uniform(low=0.0, high=1.0):
+        def _f(a):
+            return _rng.uniform(low, high, size=_np.shape(a)).astype(_np.float32)
+        return _f
+
+
+init = _Init()

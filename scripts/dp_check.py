@@ -1,0 +1,110 @@
+"""Data-parallel correctness check (torchrun, >= 2 GPUs of one box); tests/test_dp_gpu.py runs it.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dp_check.py
+
+Checks, each on every rank:
+  1. peer-exchange path (nmx_allreduce_adam inside ONE CUDA graph per iteration): ranks stay BIT-identical;
+  2. it follows the NCCL path (all-reduce -> scale -> Adam, eager) step for step (same losses to 2e-3, parameters to
+     fp32 reduction-order noise);
+  3. the DP step equals the single-process step on the concatenated global batch (gradient of the mean loss over
+     world x B rays = mean of the ranks' gradients);
+  4. render(..., process_group=) / NeRFTrainer.render_frame(process_group=) assemble a frame that is bit-identical to
+     the same frame rendered by one rank alone.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nerf_meets_mlx_b200.models.NeRF import default_args  # noqa: E402
+from nerf_meets_mlx_b200.training import NeRFTrainer  # noqa: E402
+from nerf_meets_mlx_b200.rendering import render as R  # noqa: E402
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+dev = torch.device("cuda", torch.cuda.current_device())
+dist.init_process_group("nccl", device_id=dev)
+B, ITERS = 512, 6
+args = lambda: default_args(N_importance=128, n_depth_samples=64)
+
+
+def batch(it, r):
+    g = torch.Generator(device="cuda").manual_seed(1000 * it + r)
+    o = torch.randn(B, 3, device="cuda", generator=g) * 0.2 + torch.tensor([0.0, 0.0, 4.0], device="cuda")
+    d = torch.randn(B, 3, device="cuda", generator=g) - torch.tensor([0.0, 0.0, 3.0], device="cuda")
+    t = torch.rand(B, 3, device="cuda", generator=g)
+    u = torch.rand(B, 128, device="cuda", generator=g)
+    return o, d, t, u
+
+
+def run(**kw):
+    tr = NeRFTrainer(args(), device=dev, max_rays=kw.pop("max_rays", B), **kw)
+    losses = []
+    for it in range(ITERS):
+        if tr.world == 1 and world > 1:  # single-process reference: the concatenated global batch
+            parts = [batch(it, r) for r in range(world)]
+            o, d, t, u = (torch.cat(x) for x in zip(*parts))
+        else:
+            o, d, t, u = batch(it, rank)
+        r = tr.train_iteration(o, d, t, u_vals=u)
+        losses.append((float(r["loss_coarse"]), float(r["loss_fine"])))
+    flat = torch.cat([tr.coarse.flat.data, tr.fine.flat.data]).clone()
+    return tr, losses, flat
+
+
+def same_on_all_ranks(flat, what):
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, flat), f"rank {rank}: {what}: parameters differ from rank 0"
+
+
+# 1. peer exchange, graph replay
+tr_p, loss_p, flat_p = run(use_cuda_graph=True, use_p2p=True)
+assert tr_p.xchg is not None and tr_p.xchg.error() == 0, "peer exchange reported a barrier timeout"
+assert tr_p.xchg.epoch() == 2 * ITERS, tr_p.xchg.epoch()
+assert tr_p._graph is not None and not isinstance(tr_p._graph, list)
+same_on_all_ranks(flat_p, "peer exchange")
+# 2. NCCL path, eager
+tr_n, loss_n, flat_n = run(use_cuda_graph=False, use_p2p=False)
+same_on_all_ranks(flat_n, "nccl")
+assert all(abs(a - b) <= 2e-3 * abs(a) for x, y in zip(loss_p, loss_n) for a, b in zip(x, y)), (loss_p, loss_n)
+# parameters moved by ~ITERS * lr = 3e-3 per element; the two paths may differ by reduction-order noise amplified by Adam
+d_pn = float((flat_p - flat_n).abs().max())
+assert d_pn < 2e-4, d_pn
+# 3. single-process step on the global batch (world forced to 1)
+tr_1, loss_1, flat_1 = run(use_cuda_graph=False, data_parallel=False, max_rays=B * world)
+d_p1 = float((flat_p - flat_1).abs().max())
+# the DP loss of a rank is over ITS shard; the mean over ranks is the global loss
+lp = torch.tensor(loss_p, device="cuda", dtype=torch.float64)
+dist.all_reduce(lp)
+lp = (lp / world).cpu().numpy()
+assert np.allclose(lp, np.array(loss_1), rtol=2e-3), (lp, loss_1)
+assert d_p1 < 2e-4, d_p1
+# 4. sharded render == single-rank render, bit for bit
+H = W = 40
+focal = 0.5 * W / np.tan(0.5 * 0.6911112)
+K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+from nerf_meets_mlx_b200.ops.pose import pose_spherical  # noqa: E402
+c2w = torch.as_tensor(np.asarray(pose_spherical(30.0, -30.0, 4.0), dtype=np.float32))[:3, :4].to(dev)
+kw = dict(tr_p.kw, render_rays_func=R.render_rays_eval)
+u_all = torch.rand(H * W, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+with torch.no_grad():
+    full = R.render(H, W, K, chunk=300, c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True, u_vals=u_all, **kw)
+    shard = R.render(H, W, K, chunk=300, c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True, u_vals=u_all,
+                     process_group=dist.group.WORLD, **kw)
+for a, b in zip(full[:3], shard[:3]):
+    assert a.shape == b.shape and torch.equal(a, b), "sharded render differs from the single-rank frame"
+for k in full[3]:
+    assert torch.equal(full[3][k], shard[3][k]), k
+rays = R.build_rays(H, W, K, c2w, 2.0, 6.0, use_viewdirs=True)[0]
+f1 = tr_p.render_frame(rays, chunk=300, u_vals=u_all)
+f2 = tr_p.render_frame(rays, chunk=300, u_vals=u_all, process_group=dist.group.WORLD)
+for k in f1:
+    assert torch.equal(f1[k], f2[k]), k
+print(f"rank {rank}: DP_CHECK_OK  |p2p - nccl| {d_pn:.2e}  |p2p - single| {d_p1:.2e}  losses {loss_p[-1]}", flush=True)
+tr_p.close()
+dist.barrier()
+dist.destroy_process_group()

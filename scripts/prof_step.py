@@ -6,7 +6,7 @@ from nerf_meets_mlx_b200 import ops
 from nerf_meets_mlx_b200.models.NeRF import default_args
 from nerf_meets_mlx_b200.training import NeRFTrainer, assemble_rays
 
-B, n, N = 8192, 64, 128
+B, n, N = (int(sys.argv[1]) if len(sys.argv) > 1 else 8192), 64, 128
 tr = NeRFTrainer(default_args(N_importance=N, n_depth_samples=n), device="cuda", max_rays=B)
 torch.manual_seed(0)
 o = torch.randn(B, 3, device="cuda") * 0.1 + torch.tensor([0.0, 0.0, 4.0], device="cuda")

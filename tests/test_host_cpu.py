@@ -109,10 +109,17 @@ class M:
 t.coarse, t.fine = M(), None
 t.broadcast_parameters()
 assert torch.equal(t.coarse.flat.data, torch.zeros(10)) and t.coarse.dirty
-# ray sharding: contiguous tiles cover the frame exactly once
-n = 640000; shard = (n + world - 1) // world
-lo, hi = rank * shard, min(n, (rank + 1) * shard)
-tot = torch.tensor([hi - lo]); dist.all_reduce(tot); assert int(tot) == n
+# ray-tile sharding of a frame (rendering.render(process_group=), NeRFTrainer.render_frame): contiguous tiles cover the
+# frame exactly once, and the gathered tiles reassemble to the single-process result, incl. ragged / empty last tiles
+from nerf_meets_mlx_b200.parallel import ray_tile, gather_tiles
+for n in (640000, 7, 1, 2 * 33 + 1):
+    lo, hi = ray_tile(n, rank, world)
+    tot = torch.tensor([hi - lo]); dist.all_reduce(tot); assert int(tot) == n
+    frame = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * 0.5 + 1.0   # what one process would render
+    got = gather_tiles(frame[lo:hi].clone(), n)
+    assert got.shape == frame.shape and torch.equal(got, frame), (n, rank)
+    got1 = gather_tiles(frame[lo:hi, :1].clone(), n)
+    assert torch.equal(got1, frame[:, :1])
 dist.destroy_process_group()
 print("ok", rank)
 '''

@@ -76,6 +76,34 @@ def test_hash_bit_exact(ops):
         np.testing.assert_array_equal(got, oenc.hashgrid_hash(c, T))
 
 
+def test_hashgrid_golden_reference_lines(ops, golden):
+    """Kernel == what the reference's own lines produce (golden/hashgrid.npz, see test_oracle_golden.py)."""
+    from nerf_meets_mlx_b200.encoding.multi_hash import MultiHashEncoding
+    g = golden("hashgrid")
+    c = g["hash_coords"]
+    c32 = c.astype(np.int32)  # every golden coordinate fits int32
+    assert np.array_equal(c32.astype(np.int64), c)
+    for T in (10, 14, 19, 24):
+        got = ops.hashgrid_hash(dev(c32, torch.int32), T).cpu().numpy().astype(np.int64)
+        np.testing.assert_array_equal(got, g[f"hash_T{T}"])
+    for tag in "abcd":
+        L_, nmin, nmax, F_, T = (int(v) for v in g[f"{tag}_cfg"])
+        enc = MultiHashEncoding(3, L_, nmin, nmax, F_, T, device="cuda")
+        np.testing.assert_array_equal(enc.scaled_res.cpu().numpy(), g[f"{tag}_scaled_res"])
+        assert enc.get_out_dim() == int(g[f"{tag}_out_dim"]) and enc.hash_table_size == int(g[f"{tag}_table_size"])
+    for tag in "ab":
+        L_, nmin, nmax, F_, T = (int(v) for v in g[f"call_{tag}_cfg"])
+        tables = np.random.default_rng(900 + L_).uniform(-1.0, 1.0, size=(L_, 2 ** T, F_)).astype(np.float32)
+        np.testing.assert_array_equal(tables[:, :64], g[f"call_{tag}_tables_sample"])
+        out, idx = ops.hashgrid_fwd(dev(g[f"call_{tag}_x"]), dev(tables), dev(g[f"{tag}_scaled_res"]), T, return_idx=True)
+        np.testing.assert_array_equal(idx.cpu().numpy().astype(np.int64), g[f"call_{tag}_idx"])
+        np.testing.assert_array_equal(out.cpu().numpy(), g[f"call_{tag}_out"])
+        enc = MultiHashEncoding(3, L_, nmin, nmax, F_, T, device="cuda")
+        with torch.no_grad():
+            enc.hash_table.copy_(dev(tables))
+            np.testing.assert_array_equal(enc(dev(g[f"call_{tag}_x"])).cpu().numpy(), g[f"call_{tag}_out"])
+
+
 @pytest.mark.parametrize("L,F,T", [(16, 2, 19), (4, 4, 12), (8, 1, 10)])
 def test_hashgrid_fwd_bwd(ops, L, F, T):
     rng = np.random.default_rng(3)

@@ -132,6 +132,35 @@ def test_hash_known_answers():
     assert res[0] == 16 and res.shape == (16,) and res[-1] in (2047.0, 2048.0)
 
 
+def _golden_tables(g, tag):
+    L_, _, _, F_, T = (int(v) for v in g[f"call_{tag}_cfg"])
+    tables = np.random.default_rng(900 + L_).uniform(-1.0, 1.0, size=(L_, 2 ** T, F_)).astype(np.float32)
+    np.testing.assert_array_equal(tables[:, :64], g[f"call_{tag}_tables_sample"])  # same stream as the generator's
+    return tables
+
+
+def test_hashgrid_pinned_to_reference_lines(golden):
+    """tests/golden/hashgrid.npz holds what the reference's OWN lines produce (oracle/make_golden.py): the real
+    constructor's scaled_res / growing_factor (multi_hash.py:32-43), `hash` (:61-77) on int64 coordinates incl.
+    negatives, and `__call__` (:79-137) with only the eight list-call lookup lines replaced by a per-level lookup."""
+    g = golden("hashgrid")
+    for tag in "abcd":
+        L_, nmin, nmax, F_, T = (int(v) for v in g[f"{tag}_cfg"])
+        np.testing.assert_array_equal(oenc.hashgrid_scaled_res(L_, nmin, nmax), g[f"{tag}_scaled_res"])
+        assert int(g[f"{tag}_table_size"]) == 1 << T and int(g[f"{tag}_out_dim"]) == L_ * F_
+    c = g["hash_coords"]
+    assert c.min() < 0 and c.max() > 2 ** 30
+    for T in (10, 14, 19, 24):
+        np.testing.assert_array_equal(oenc.hashgrid_hash(c, T), g[f"hash_T{T}"])  # bit-exact (Appendix C)
+    for tag in "ab":
+        L_, nmin, nmax, F_, T = (int(v) for v in g[f"call_{tag}_cfg"])
+        tables = _golden_tables(g, tag)
+        res = oenc.hashgrid_scaled_res(L_, nmin, nmax)
+        idx, _ = oenc.hashgrid_corner_indices(g[f"call_{tag}_x"], res, T)
+        np.testing.assert_array_equal(idx, g[f"call_{tag}_idx"])      # corner order and cell indices: bit-exact
+        np.testing.assert_array_equal(oenc.hashgrid_encode(g[f"call_{tag}_x"], tables, res, T), g[f"call_{tag}_out"])
+
+
 # ------------------------------------------------------------------ SURVEY 8f rows (next to the hot path)
 def test_sh_and_identity(golden):
     g = golden("sh")
