@@ -42,3 +42,28 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream);
 int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out, cudaStream_t stream);
 
 }  // namespace nmx
+
+namespace nmx {
+
+// ---- batched weight gradients: every wgrad of one backward pass in ONE launch (nmx_wgrad_batch.cu).
+// All operands live in at most four row-major bf16 tensors (the saved-activation region, the saved-dY region, the
+// encoded-input tile X0 and d_hd), addressed per job by (tensor, first row, first column).
+constexpr int kMaxWgradJobs = 12;
+struct WgradBatchTensor { const void* base; int64_t rows; int cols; };  // row-major bf16 [rows, cols], ld = cols
+struct WgradBatchJob {
+  int dy_t, x_t, x2_t;           // tensor indices (x2_t < 0: no second operand)
+  int64_t dy_row0, x_row0, x2_row0;
+  int dy_col, x_col, x2_col;
+  int M, N;                      // dW rows (multiple of 64, <= 256), first-operand width (multiple of 64, <= 256)
+  float* dW; int ldw, w_col, n_valid;
+  float* db;                     // optional bias gradient [M]
+  float* dW2; int ldw2, w2_col, n_valid2;  // second operand: 64 columns of tensor x2_t
+};
+struct WgradBatchDesc {
+  int n_tensors; WgradBatchTensor t[4];
+  int n_jobs; WgradBatchJob job[kMaxWgradJobs];
+  int64_t P;                     // points (contraction length), the same for every job
+};
+int launch_wgrad_batch(const WgradBatchDesc& d, cudaStream_t stream);
+
+}  // namespace nmx

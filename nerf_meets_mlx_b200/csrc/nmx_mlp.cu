@@ -1096,13 +1096,60 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
         return launch_wgrad(g, sw);
       };
       const bool dual_ok = (W == 256) && p->dir_pad == 64 && p->pos_pad == 64 && !getenv("NMX_DISABLE_DUAL_WGRAD");
-      if (dual_ok) {
+      // One launch for all layers pays off where the per-launch fixed cost (148 partial-tile flushes + tail, ~11 us x 18)
+      // matters: small passes (a 1024-ray shard).  Large passes stream each layer at the HBM roofline either way.
+      static int64_t batch_max_points = -1;
+      if (batch_max_points < 0) {
+        const char* e = getenv("NMX_WGRAD_BATCH_MAX_POINTS");
+        batch_max_points = e ? atoll(e) : 200000;  // measured on B200: faster up to ~200 k points, slower from ~400 k
+        if (getenv("NMX_DISABLE_WGRAD_BATCH")) batch_max_points = 0;
+      }
+      const bool batched = dual_ok && K == 1 && P <= batch_max_points && p->D + 1 <= kMaxWgradJobs;
+      if (batched) {
+        // every weight gradient of the pass in ONE launch: the SMs are divided among the layers (nmx_wgrad_batch.cu)
+        WgradBatchDesc bd;
+        memset(&bd, 0, sizeof(bd));
+        const int64_t cap = p->max_points;
+        bd.n_tensors = 4;
+        bd.t[0] = {c.act + c.al.h0, (int64_t)(p->D + 1) * cap, W};      // saved activations h_0 .. h_{D-1} (+ feature slot)
+        bd.t[1] = {c.G(0), (int64_t)(p->D + 1) * cap, W};                // saved data gradients dY_0 .. dY_{D-1}
+        bd.t[2] = {c.X0(), P, p->x0_cols};                               // encoded inputs [PE(pos) | PE(dir)]
+        bd.t[3] = {c.GHD(), P, W / 2};                                   // d_hd
+        bd.P = P;
+        int nj = 0;
+        {  // dir layer: G = d_hd^T h_{D-1} (folded below) and the dir-PE columns of dW_dir from one read of d_hd
+          WgradBatchJob& g = bd.job[nj++];
+          g.dy_t = 3; g.dy_row0 = 0; g.dy_col = 0; g.x_t = 0; g.x_row0 = (int64_t)(p->D - 1) * cap; g.x_col = 0;
+          g.x2_t = 2; g.x2_row0 = 0; g.x2_col = p->pos_pad;
+          g.M = W / 2; g.N = W; g.dW = gfold; g.ldw = W; g.w_col = 0; g.n_valid = W; g.db = d_params + p->dir.b_off;
+          g.dW2 = dWd; g.ldw2 = p->dir.in; g.w2_col = W; g.n_valid2 = p->in_dir;
+        }
+        for (int l = p->D - 1; l >= 0; --l) {
+          const LinearRef& r = p->trunk[l];
+          WgradBatchJob& g = bd.job[nj++];
+          g.dy_t = 1; g.dy_row0 = (int64_t)l * cap; g.dy_col = 0; g.M = W; g.x2_t = -1;
+          g.dW = d_params + r.w_off; g.ldw = r.in; g.db = d_params + r.b_off;
+          if (l == 0) {
+            g.x_t = 2; g.x_row0 = 0; g.x_col = 0; g.N = p->pos_pad; g.w_col = 0; g.n_valid = p->in_pos;
+          } else {
+            g.x_t = 0; g.x_row0 = (int64_t)(l - 1) * cap; g.x_col = 0; g.N = W; g.n_valid = W;
+            if (r.in == W + p->in_pos) {  // skip layer: [x_pos | h] against one read of dY
+              g.w_col = p->in_pos;
+              g.x2_t = 2; g.x2_row0 = 0; g.x2_col = 0; g.dW2 = g.dW; g.ldw2 = r.in; g.w2_col = 0; g.n_valid2 = p->in_pos;
+            } else {
+              g.w_col = 0;
+            }
+          }
+        }
+        bd.n_jobs = nj;
+        if ((rc = launch_wgrad_batch(bd, sw))) return rc;
+      } else if (dual_ok) {
         if ((rc = wg2(c.GHD(), W / 2, hl, W / 2, gfold, W, 0, d_params + p->dir.b_off, p->pos_pad, p->in_dir, dWd, p->dir.in, W))) return rc;
       } else {
         if ((rc = wg(c.GHD(), W / 2, hl, W, 0, W / 2, W, W, gfold, W, 0, d_params + p->dir.b_off))) return rc;
         if ((rc = wg(c.GHD(), W / 2, c.X0(), p->x0_cols, p->pos_pad, W / 2, p->dir_pad, p->in_dir, dWd, p->dir.in, W, nullptr))) return rc;
       }
-      for (int l = p->D - 1; l >= 0; --l) {
+      for (int l = p->D - 1; l >= 0 && !batched; --l) {
         const LinearRef& r = p->trunk[l];
         const bf16* dY = c.G(l);
         float* dW = d_params + r.w_off;

@@ -7,6 +7,8 @@ from . import Encoding
 
 def mlx_linspace(start, stop, num):
     """mx.linspace as assumed for MLX 0.7.0: arange(num) * fp32((stop-start)/(num-1)) + start, all fp32."""
+    if num == 1:  # mx.linspace(a, b, num=1) is [a] (no division by num - 1)
+        return torch.tensor([float(start)], dtype=torch.float32)
     seq = torch.arange(num, dtype=torch.float32)
     step = torch.tensor((float(stop) - float(start)) / (num - 1), dtype=torch.float32)
     return seq * step + torch.tensor(float(start), dtype=torch.float32)

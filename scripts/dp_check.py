@@ -71,18 +71,30 @@ same_on_all_ranks(flat_p, "peer exchange")
 tr_n, loss_n, flat_n = run(use_cuda_graph=False, use_p2p=False)
 same_on_all_ranks(flat_n, "nccl")
 assert all(abs(a - b) <= 2e-3 * abs(a) for x, y in zip(loss_p, loss_n) for a, b in zip(x, y)), (loss_p, loss_n)
-# parameters moved by ~ITERS * lr = 3e-3 per element; the two paths may differ by reduction-order noise amplified by Adam
-d_pn = float((flat_p - flat_n).abs().max())
-assert d_pn < 2e-4, d_pn
+# MLX-style Adam without bias correction moves EVERY element by ~3 lr per early step whatever |g| is, so an element whose
+# tiny gradient changes sign with the summation order differs by O(ITERS * lr); such elements must stay rare, and the
+# bulk of the two parameter vectors must agree to fp32 noise
+
+
+def close(a, b, what):
+    d = (a - b).abs()
+    frac = float((d > 1e-4).float().mean())
+    rel = float(d.norm() / (a - flat_0).norm().clamp_min(1e-30))
+    assert frac < 2e-2 and rel < 5e-2, (what, frac, rel)
+    return rel
+
+
+tr_0 = NeRFTrainer(args(), device=dev, max_rays=128, data_parallel=False)
+flat_0 = torch.cat([tr_0.coarse.flat.data, tr_0.fine.flat.data]).clone()  # the common initial parameters
+d_pn = close(flat_p, flat_n, "p2p vs nccl")
 # 3. single-process step on the global batch (world forced to 1)
 tr_1, loss_1, flat_1 = run(use_cuda_graph=False, data_parallel=False, max_rays=B * world)
-d_p1 = float((flat_p - flat_1).abs().max())
 # the DP loss of a rank is over ITS shard; the mean over ranks is the global loss
 lp = torch.tensor(loss_p, device="cuda", dtype=torch.float64)
 dist.all_reduce(lp)
 lp = (lp / world).cpu().numpy()
 assert np.allclose(lp, np.array(loss_1), rtol=2e-3), (lp, loss_1)
-assert d_p1 < 2e-4, d_p1
+d_p1 = close(flat_p, flat_1, "p2p vs single process")
 # 4. sharded render == single-rank render, bit for bit
 H = W = 40
 focal = 0.5 * W / np.tan(0.5 * 0.6911112)
@@ -92,9 +104,9 @@ c2w = torch.as_tensor(np.asarray(pose_spherical(30.0, -30.0, 4.0), dtype=np.floa
 kw = dict(tr_p.kw, render_rays_func=R.render_rays_eval)
 u_all = torch.rand(H * W, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
 with torch.no_grad():
-    full = R.render(H, W, K, chunk=300, c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True, u_vals=u_all, **kw)
-    shard = R.render(H, W, K, chunk=300, c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True, u_vals=u_all,
-                     process_group=dist.group.WORLD, **kw)
+    # kw is create_NeRF's render_kwargs (use_viewdirs, ndc=False, white_bkgd, networks, query fn ...)
+    full = R.render(H, W, K, chunk=300, c2w=c2w, near=2.0, far=6.0, u_vals=u_all, **kw)
+    shard = R.render(H, W, K, chunk=300, c2w=c2w, near=2.0, far=6.0, u_vals=u_all, process_group=dist.group.WORLD, **kw)
 for a, b in zip(full[:3], shard[:3]):
     assert a.shape == b.shape and torch.equal(a, b), "sharded render differs from the single-rank frame"
 for k in full[3]:
@@ -104,7 +116,7 @@ f1 = tr_p.render_frame(rays, chunk=300, u_vals=u_all)
 f2 = tr_p.render_frame(rays, chunk=300, u_vals=u_all, process_group=dist.group.WORLD)
 for k in f1:
     assert torch.equal(f1[k], f2[k]), k
-print(f"rank {rank}: DP_CHECK_OK  |p2p - nccl| {d_pn:.2e}  |p2p - single| {d_p1:.2e}  losses {loss_p[-1]}", flush=True)
+print(f"rank {rank}: DP_CHECK_OK  rel. update difference p2p vs nccl {d_pn:.2e}, vs single process {d_p1:.2e}  losses {loss_p[-1]}", flush=True)
 tr_p.close()
 dist.barrier()
 dist.destroy_process_group()
