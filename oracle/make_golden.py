@@ -94,6 +94,54 @@ def main():
                   f"{tag}_cdf": cdf.numpy(), f"{tag}_inds": inds.numpy()})
     np.savez_compressed(os.path.join(OUT, "sample_pdf.npz"), **g)
 
+    # ---- larger resampling golden: 2048 rays x 128 draws through the REAL reference function, weights shaped
+    # like trained compositing weights (a few peaks over a small floor), plus the end-to-end index-mismatch count of the
+    # canonical CDF (fp64 sum / prefix, oracle + kernels) against the reference's own torch-CPU CDF over > 10^7 draws
+    # (torch-CPU `sum` has an ISA-dependent fp32 order: this container's AVX512 host; SURVEY 7 probed ~1.2e-6).
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import sampling as osamp
+    rng_s = np.random.default_rng(20261020)
+
+    def peaky(B, n):
+        w = 0.002 * rng_s.random(size=(B, n, 1))
+        for _ in range(3):
+            c = rng_s.integers(0, n, size=B)
+            w[np.arange(B), c, 0] += rng_s.random(size=B) ** 2
+            w[np.arange(B), np.minimum(c + 1, n - 1), 0] += 0.5 * rng_s.random(size=B) ** 2
+        return w.astype(np.float32)
+
+    def ref_draw(z, w, seed, N):
+        torch.manual_seed(seed)
+        u = torch.rand([z.shape[0], N])
+        torch.manual_seed(seed)
+        out = sampling.sample_from_inverse_cdf_torch(torch.from_numpy(z), torch.from_numpy(w), N)
+        wt = torch.from_numpy(w)[..., 0] + 0.01
+        pdf = wt / torch.sum(wt, dim=-1, keepdim=True)
+        cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, axis=-1))
+        cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+        inds = torch.searchsorted(cdf, u, side="right")
+        return u.numpy(), out.numpy(), inds.numpy()
+
+    B, n, N = 2048, 64, 128
+    z = np.sort(rng_s.uniform(2.0, 6.0, size=(B, n)).astype(np.float32), axis=-1)
+    w = peaky(B, n)
+    u, out, inds = ref_draw(z, w, 777, N)
+    o_out, o_inds = osamp.sample_pdf(z, w, u, return_inds=True)
+    g = {"z": z, "w": w, "u": u, "out": out, "inds": inds.astype(np.uint8),
+         "mismatch_2048": np.int64(np.sum(o_inds != inds))}
+    tot = mism = 0
+    for k in range(10):  # 10 x 8192 rays x 128 draws = 10.5 M draws
+        zb = np.sort(rng_s.uniform(2.0, 6.0, size=(8192, n)).astype(np.float32), axis=-1)
+        wb = peaky(8192, n) if k % 2 else rng_s.random(size=(8192, n, 1)).astype(np.float32)
+        ub, _, ib = ref_draw(zb, wb, 1000 + k, N)
+        _, ob = osamp.sample_pdf(zb, wb, ub, return_inds=True)
+        tot += ib.size
+        mism += int(np.sum(ob != ib))
+    g["big_draws"], g["big_mismatch"] = np.int64(tot), np.int64(mism)
+    print(f"sample_pdf: canonical-CDF vs reference-CDF index mismatches: {mism} of {tot} draws ({mism / tot:.2e}); "
+          f"2048-ray golden: {int(g['mismatch_2048'])} of {B * N}")
+    np.savez_compressed(os.path.join(OUT, "sample_pdf_large.npz"), **g)
+
     # ---- PE flavour A (models/embedding.py) and embed()
     pos = rng.uniform(-4.0, 4.0, size=(6, 5, 3)).astype(np.float32)
     dirs = rng.standard_normal(size=(6, 3)).astype(np.float32)

@@ -131,7 +131,7 @@ def test_c4_hashgrid_tiny_mlp_step_vs_oracle():
 
 
 @pytest.mark.parametrize("cfg_id", [0, 2, 3])
-def test_mlp_input_gradient_vs_oracle(cfg_id):
+def test_mlp_input_gradient_vs_oracle(cfg_id, measured):
     """nmx_mlp_bwd_input: d loss / d (encoded position inputs) through the fused chain (view-dir 8x256 net, skip
     connection: two contributions), the layer-by-layer path with a skip (image net) and the tiny 3x64 net."""
     from test_mlp_gpu import CFGS, emulated_forward, make_pair
@@ -154,6 +154,7 @@ def test_mlp_input_gradient_vs_oracle(cfg_id):
     assert float((got - x_emu.grad[:, :n_pos]).norm() / x_emu.grad[:, :n_pos].norm()) < 1e-2
     # vs the fp32 oracle: units whose pre-activation rounds across zero flip their ReLU mask (same bound as the
     # parameter gradients in test_mlp_gpu.py)
-    assert float((got - x_ref.grad[:, :n_pos]).norm() / x_ref.grad[:, :n_pos].norm()) < 1.5e-1
+    e = measured(f"mlp_input_grad_vs_fp32_oracle/cfg{cfg_id}", float((got - x_ref.grad[:, :n_pos]).norm() / x_ref.grad[:, :n_pos].norm()))
+    assert e < 1.5e-1
     if cin > n_pos:  # declared: view-direction inputs receive no gradient (nothing learnable feeds them)
         assert float(x_dev.grad[:, n_pos:].abs().max()) == 0.0

@@ -87,9 +87,13 @@ CFGS = [
 ]
 
 
+# normwise gradient error vs the fp32 oracle: 2x the largest value measured on B200 (profiles/r2_test_measurements.json)
+GRAD_VS_FP32 = {1000: 1.5e-1, 128: 1.5e-1}
+
+
 @pytest.mark.parametrize("cfg", CFGS)
 @pytest.mark.parametrize("P", [1000, 128])
-def test_forward_backward_vs_oracle(cfg, P):
+def test_forward_backward_vs_oracle(cfg, P, measured):
     torch.manual_seed(P)
     ref, net = make_pair(**cfg)
     cin = cfg["channel_input"] + (cfg["channel_input_views"] if cfg["is_use_view_directions"] else 0)
@@ -112,8 +116,8 @@ def test_forward_backward_vs_oracle(cfg, P):
     for n, gr, ge in zip(names, g_ref, g_emu):
         en = rel_norm(got[n].cpu(), ge)
         assert en < 1e-2, f"grad {n}: normwise rel err vs bf16-emulating reference {en}"
-        ef = rel_norm(got[n].cpu(), gr)
-        assert ef < 1.5e-1, f"grad {n}: normwise rel err vs fp32 oracle {ef}"
+        ef = measured(f"mlp_grad_vs_fp32_oracle/W{cfg['width_layers']}_P{P}", rel_norm(got[n].cpu(), gr))
+        assert ef < GRAD_VS_FP32[P], f"grad {n}: normwise rel err vs fp32 oracle {ef}"
 
 
 def test_forward_golden_noview(golden):

@@ -19,7 +19,7 @@ def _rays(B, seed=0):
     return o, d.astype(np.float32), target
 
 
-def test_train_iteration_vs_oracle():
+def test_train_iteration_vs_oracle(measured):
     from nerf_meets_mlx_b200.training import NeRFTrainer
     from nerf_meets_mlx_b200.models.NeRF import default_args
     B, n, N = 96, 64, 128
@@ -46,7 +46,7 @@ def test_train_iteration_vs_oracle():
     # gradients (bf16 operands vs the fp32 oracle; the tight check lives in test_mlp_gpu.py)
     gc = tr.coarse.split_flat(tr._g_coarse)
     for name, g in ref["grads_coarse"].items():
-        e = float((gc[name].cpu() - g).norm() / (g.norm() + 1e-20))
+        e = measured("train_iteration_96rays/coarse_grad_vs_fp32_oracle", float((gc[name].cpu() - g).norm() / (g.norm() + 1e-20)))
         assert e < 1.5e-1, (name, e)
     # fine depths: sorted, same count, close to the oracle's (weights come from a bf16 coarse net)
     zf = out["z_fine"].cpu().numpy()
@@ -84,7 +84,7 @@ def _load(net, g, prefix):
     net.load_reference_parameters({k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)})
 
 
-def test_render_api_shapes_and_coarse_fine():
+def test_render_api_shapes_and_coarse_fine(measured):
     """Mirror API (create_NeRF -> render) end to end at small size vs the oracle with identical weights."""
     from nerf_meets_mlx_b200.models.NeRF import create_NeRF, default_args
     from nerf_meets_mlx_b200.rendering import render as R
@@ -113,8 +113,8 @@ def test_render_api_shapes_and_coarse_fine():
                        network_query_fn=qf, n_depth_samples=64, N_importance=128, white_bkgd=True, u_vals=u)
     for got, want, name in ((rgb, ref[0], "rgb"), (acc, ref[2], "acc"), (extras["rgb_coarse"], ref[3]["rgb_coarse"], "rgb_coarse")):
         want = want.numpy()
-        err = np.abs(got.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-6)
-        assert err < 2e-2, (name, err)
+        err = measured(f"render_12x16/{name}", np.abs(got.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-6))
+        assert err < 1e-2, (name, err)  # north_star: 1e-2 for bf16 MLP outputs
 
 
 @pytest.mark.gpu
