@@ -28,7 +28,9 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, experiments=False):
+    """experiments=True adds -DNMX_EXPERIMENTS: the timing switches of the chain kernels (NMX_CHAIN_DBG, NMX_CHAIN2_DBG ...:
+    they skip work and produce garbage) are compiled in; the default build has none of them."""
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = sources()
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -38,12 +40,12 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(OUT_DIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        if force or _stale(o, [s] + hdrs):
+        if force or experiments or _stale(o, [s] + hdrs):
             jobs.append((s, o))
 
     def compile_one(job):
         s, o = job
-        cmd = [NVCC] + FLAGS + ["-c", s, "-o", o]
+        cmd = [NVCC] + FLAGS + (["-DNMX_EXPERIMENTS"] if experiments else []) + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OUT_DIR, os.path.basename(s)[:-3] + ".ptxas.log")
         with open(log, "w") as f:
@@ -66,4 +68,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

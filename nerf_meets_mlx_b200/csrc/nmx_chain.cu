@@ -292,7 +292,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = s_ring + stage * kSlabBytes;
           if (elect_one()) {
-            if (prm.dbg & 1) {  // experiment: no weight traffic (operands are whatever the ring holds)
+            if NMX_DBG(prm, 1) {  // experiment: no weight traffic (operands are whatever the ring holds)
               mbar_arrive(&full[stage]);
             } else {
               mbar_arrive_expect_tx(&full[stage], (uint32_t)N * 128u);
@@ -334,7 +334,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     int it = 0;
     uint32_t lcount = 0;
     uint32_t acbits = 0;  // bit c = parity of the number of signals so far on act_ready[c] (same replay in every role)
-    const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && lane == 0;
+    const bool tr_on = NMX_DBG(prm, 4) && blockIdx.x == 0 && lane == 0;
     const uint32_t smem16 = smem_u32(smem) >> 4;
     const uint32_t ring16 = smem_u32(s_ring) >> 4;
     constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;  // SBO 1024 B, descriptor version 1, SWIZZLE_128B
@@ -405,7 +405,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
         if (MODE == 1) {  // step A: d_hd (chunks 0,1) -> its own [P, 128] buffer
           for (int c = 0; c < 2; ++c) {
             mbar_wait(&act_ready[c], (acbits >> c) & 1u);
-            if (elect_one() && !(prm.dbg & 16)) {
+            if (elect_one() && !NMX_DBG(prm, 16)) {
               tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
               tma_store_commit();
             }
@@ -424,8 +424,8 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           const int row0 = prm.L[l].save_row0 + tile * 128;
           for (int c = 0; c < nck; ++c) {
             mbar_wait(&act_ready[c], (acbits >> c) & 1u);
-            if (elect_one() && !(prm.dbg & 16)) {
-              if (kind == 1 && (prm.dbg & 32))  // experiment: chunk-major planes, each store one contiguous 16 KB block
+            if (elect_one() && !NMX_DBG(prm, 16)) {
+              if (kind == 1 && NMX_DBG(prm, 32))  // experiment: chunk-major planes, each store one contiguous 16 KB block
                 tma_store_2d(&maps.save, s_act + c * kChunkBytes, 0, prm.L[l].save_row0 * 4 + c * prm.cap + tile * 128);
               else if (kind == 1) tma_store_2d(&maps.save, s_act + c * kChunkBytes, c * 64, row0);
               else if (kind == 2) tma_store_2d(&maps.hd, s_act + c * kChunkBytes, c * 64, tile * 128);
@@ -435,7 +435,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
           }
           acbits ^= (nck == 4 ? 0xFu : 0x3u);
           if (MODE == 0 && prm.bits != nullptr && prm.L[l].bits_row0 >= 0) {
-            if (elect_one() && !(prm.dbg & 16)) {  // the layer's ReLU sign bits: one contiguous 4 KB tile
+            if (elect_one() && !NMX_DBG(prm, 16)) {  // the layer's ReLU sign bits: one contiguous 4 KB tile
               bulk_store_1d(prm.bits + ((size_t)prm.L[l].bits_row0 + (size_t)tile * 128) * 8, s_bits, kBitsBytes);
               tma_store_commit();
             }
@@ -527,7 +527,7 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       if (save && leader) tma_store_wait<0>();
       __syncwarp();
     }
-    if (MODE == 1 && warp == kMaskWarp && !(prm.dbg & 8)) {
+    if (MODE == 1 && warp == kMaskWarp && !NMX_DBG(prm, 8)) {
       uint32_t step = 0;
       auto fill = [&](int row0) {
         const uint32_t slot = step & 1u;
@@ -556,9 +556,9 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
     if constexpr (MODE == 0) {
       const uint32_t bias_base = smem_u32(s_bias);
       const uint32_t w7_addr = smem_u32(s_w7), wrgb_addr = smem_u32(s_wrgb);
-      const bool skip_math = (prm.dbg & 2) != 0;
+      const bool skip_math = NMX_DBG(prm, 2) != 0;
       uint32_t lcount = 0;
-      const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+      const bool tr_on = NMX_DBG(prm, 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
       const bool vd = prm.rgb_layer >= 0;
       float hb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // head biases of the view-dir net (rgb, alpha), loaded once
       if (vd && part == 0) {
@@ -657,8 +657,8 @@ mlp_chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams prm) 
       // ---------------------------------------------------- backward data-gradient epilogue
       const uint32_t wa_addr = smem_u32(s_w7);      // w_alpha [256] fp32
       const uint32_t wrgb_addr = smem_u32(s_wrgb);  // w_rgb [3][128] fp32
-      const bool tr_on = (prm.dbg & 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
-      const bool no_mask = (prm.dbg & 8) != 0;  // experiment: skip the saved-activation reads
+      const bool tr_on = NMX_DBG(prm, 4) && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0;
+      const bool no_mask = NMX_DBG(prm, 8) != 0;  // experiment: skip the saved-activation reads
       uint32_t lcount = 0, scount = 0;
       uint32_t mstep = 0;  // masked steps so far (step A + masked layers): slot = mstep & 1, parity = (mstep >> 1) & 1
       const uint32_t bits_base = smem_u32(s_bits) + (uint32_t)row_local * 32u;
@@ -808,12 +808,11 @@ static int launch_chain(const ChainMaps& maps, const ChainParams& prm_in, cudaSt
     }
     d.n_pieces = d.n_slabs;
   }
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (once_per_device(attr)) {
     NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<MODE>::kAlloc));
     if (MODE == 0)
       NMX_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<0>::kAlloc));
-    attr = true;
   }
   int tiles = (prm.P + 127) / 128;
   const int cap_ctas = (prm.max_ctas > 0 && prm.max_ctas < kNumSMs) ? prm.max_ctas : kNumSMs;

@@ -159,7 +159,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           const uint32_t bytes = (uint32_t)half_rows * 128u;
           for (int t = 0; t < (valid_y ? 2 : 1); ++t) {
             for (int s = 0; s < layer_slabs(l); ++s) {
-              if (prm.dbg & 256) {  // experiment: non-suspending poll
+              if NMX_DBG(prm, 256) {  // experiment: non-suspending poll
                 uint32_t ok;
                 do {
                   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -168,27 +168,27 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               } else {
                 mbar_wait(&empty[stage], phase ^ 1);
               }
-              if (prm.dbg & 4) {  // experiment: no weight traffic (results are garbage)
+              if NMX_DBG(prm, 4) {  // experiment: no weight traffic (results are garbage)
                 if (leader_cta) mbar_arrive(&full[stage]);
-              } else if (prm.dbg & 16) {  // experiment: only the leader loads its half (results are garbage)
+              } else if NMX_DBG(prm, 16) {  // experiment: only the leader loads its half (results are garbage)
                 if (leader_cta) {
                   mbar_arrive_expect_tx(&full[stage], bytes);
                   tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64, 0);
                 }
-              } else if (prm.dbg & 64) {  // experiment: both load, CTA 1's completion stays local (leader does not wait for it)
+              } else if NMX_DBG(prm, 64) {  // experiment: both load, CTA 1's completion stays local (leader does not wait for it)
                 mbar_arrive_expect_tx(&full[stage], bytes);
                 tma_load_2d(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64, (int)rank * half_rows);
-              } else if (prm.dbg & 32) {  // experiment: only CTA 1 loads its half
+              } else if NMX_DBG(prm, 32) {  // experiment: only CTA 1 loads its half
                 if (leader_cta) mbar_arrive_expect_tx(&full[stage], bytes);
                 else tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64, half_rows);
-              } else if (prm.dbg & 1024) {  // experiment: ONE tensor map for every layer (descriptor-cache test)
+              } else if NMX_DBG(prm, 1024) {  // experiment: ONE tensor map for every layer (descriptor-cache test)
                 if (leader_cta) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
                 tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l == kNL - 1 ? kNL - 1 : 1], &full[stage],
                                  (s & 3) * 64, (int)rank * half_rows);
               } else {
                 if (leader_cta) mbar_arrive_expect_tx(&full[stage], 2 * bytes);
                 tma_load_2d_pair(smem + Smem2::kRingOff + stage * kHalfSlab, &maps.w[l], &full[stage], s * 64,
-                                 (prm.dbg & 128) ? 0 : (int)rank * half_rows);
+                                 NMX_DBG(prm, 128) ? 0 : (int)rank * half_rows);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -216,7 +216,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
           const int ns = layer_slabs(l);
           for (int t = 0; t < (valid_y ? 2 : 1); ++t) {
             mbar_wait(&tempty[t], (lc[t] & 1u) ^ 1u);  // the previous layer's epilogue has drained this accumulator
-            if (!(prm.dbg & 4096)) mbar_wait_cluster(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
+            if (!NMX_DBG(prm, 4096)) mbar_wait_cluster(&tempty_peer[t], (lc[t] & 1u) ^ 1u);  // ... in CTA 1 as well
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)t * 256u;
             for (int s = 0; s < ns; ++s) {
@@ -225,7 +225,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               if (src == 4) mbar_wait_cluster(&pos_full[t], tc[t] & 1u);
               else {
                 mbar_wait(&act_ready[t * 4 + src], (gen[t] - 1u) & 1u);
-                if (!(prm.dbg & 4096)) mbar_wait_cluster(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
+                if (!NMX_DBG(prm, 4096)) mbar_wait_cluster(&act_peer[t * 4 + src], (gen[t] - 1u) & 1u);
               }
               tc_fence_after();
               const uint32_t a16 = smem16 + (uint32_t)((t * 5 + src) * (kChunk >> 4));
@@ -251,7 +251,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
         }
       }
     }
-    if (!leader_cta && !(prm.dbg & 4096)) {
+    if (!leader_cta && !NMX_DBG(prm, 4096)) {
       // ---- CTA 1: this warp relays the local epilogue barriers to the leader, ONE remote arrival per barrier phase
       // (sixteen warps arriving remotely with cluster-scope release semantics each was measurably slow)
       const uint32_t tempty_peer_leader = mapa_u32(smem_u32(&tempty_peer[0]), 0);
@@ -290,7 +290,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
       if (tile >= num_pt) break;
       if (tcnt > 0) mbar_wait(&pos_empty[t], (tcnt - 1u) & 1u);
 #pragma unroll 1
-      for (int rr = 0; rr < ((prm.dbg & 1) ? 0 : 4); ++rr) {
+      for (int rr = 0; rr < (NMX_DBG(prm, 1) ? 0 : 4); ++rr) {
         const int row_local = rr * 32 + lane;
         const long long row = (long long)tile * 256 + (long long)rank * 128 + row_local;
         encode_pos_row(prm.rays, prm.ray_stride, prm.z, prm.p0 + row, prm.n_per_ray, row < prm.P,
@@ -338,9 +338,9 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
             const long long rr = row < prm.P ? row : (long long)prm.P - 1;
             dbias = prm.dir_bias + ((prm.p0 + rr) / prm.n_per_ray - prm.b0) * 128;
           }
-          if (!(prm.dbg & 2048)) mbar_wait(&tfull[t], lc[t] & 1u);  // 2048: experiment, no tfull polling (garbage results)
+          if (!NMX_DBG(prm, 2048)) mbar_wait(&tfull[t], lc[t] & 1u);  // 2048: experiment, no tfull polling (garbage results)
           tc_fence_after();
-          if (prm.dbg & 512) {  // experiment: barrier traffic only (no TMEM loads, no proxy fences)
+          if NMX_DBG(prm, 512) {  // experiment: barrier traffic only (no TMEM loads, no proxy fences)
             for (int h = 0; h < nsteps / 2; ++h) {
               __syncwarp();
               if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + 2 * h + (part >> 1)]);
@@ -369,7 +369,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[t]);
             }
-            if (prm.dbg & 2) {
+            if NMX_DBG(prm, 2) {
             } else if (l == kNL - 1) {  // per-ray view-dir term of the dir layer
 #pragma unroll
               for (int i4 = 0; i4 < 8; ++i4) {
@@ -388,7 +388,7 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
               epi_cols<true, 0, 4, false, false>(r32, c, c0, 4 * sub, 0, bias_addr, act_row_addr, swz, 0u, 0, hp, rgbp, 0u);
             }
             if (h + 1 < nh) tmem_ld_32x32(tacc + (uint32_t)(c0 + 128), r32);
-            if (!(prm.dbg & 8192)) fence_proxy_async_smem();  // 8192: timing experiment without the proxy fence
+            if (!NMX_DBG(prm, 8192)) fence_proxy_async_smem();  // 8192: timing experiment without the proxy fence
             __syncwarp();
             if (l < kNL - 1 && lane == 0) mbar_arrive(&act_ready[t * 4 + c]);
           }
@@ -488,7 +488,7 @@ int launch_chain2(const Chain2Launch& a, cudaStream_t stream) {
   prm.alpha_w_off = a.alpha_w_off; prm.alpha_b_off = a.alpha_b_off; prm.rgb_w_off = a.rgb_w_off; prm.rgb_b_off = a.rgb_b_off;
   prm.rays = a.rays; prm.ray_stride = a.ray_stride; prm.z = a.z; prm.p0 = a.p0; prm.b0 = a.p0 / a.n_per_ray;
   prm.n_per_ray = a.n_per_ray; prm.dir_bias = a.dir_bias;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("NMX_CHAIN2_DBG"); dbg = e ? atoi(e) : 0; } prm.dbg = dbg; }
+  { static int dbg = -1; if (dbg < 0) dbg = experiment_env("NMX_CHAIN2_DBG"); prm.dbg = dbg; }
   // scratch: [constants block (13 KB, 256 B aligned) | per-ray dir bias]
   float* consts = a.dir_bias;
   float* dir_bias = a.dir_bias + 3328;
@@ -500,10 +500,9 @@ int launch_chain2(const Chain2Launch& a, cudaStream_t stream) {
   dir_bias_kernel<<<(unsigned)(n_rays < kNumSMs * 8 ? n_rays : kNumSMs * 8), 128, 0, stream>>>(
       a.rays, a.ray_stride, prm.b0, n_rays, a.n_freqs_dir, a.params + a.dir_w_off, a.dir_ldw, 256, dir_bias);
   NMX_LAUNCH_CHECK();
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[64] = {};
+  if (once_per_device(attr)) {
     NMX_CUDA(cudaFuncSetAttribute(mlp_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kAlloc));
-    attr = true;
   }
   const int num_pt = (int)((a.P + 255) / 256);
   int clusters = (num_pt + 1) / 2;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/nmx.h"
 
@@ -44,6 +45,25 @@ int debug_sync(const char* func, int line);
 
 constexpr int kNumSMs = 148;  // B200
 
+// Timing experiments inside the product kernels ("skip the epilogue math", "no weight traffic", event traces ...) exist
+// only in builds with -DNMX_EXPERIMENTS (python -m nerf_meets_mlx_b200.build --experiments).  In the default build
+// NMX_DBG() is the constant 0, every such branch is compiled out, and no environment variable can reach a kernel.
+#ifdef NMX_EXPERIMENTS
+#define NMX_DBG(prm, bits) (((prm).dbg & (bits)) != 0)
+#else
+#define NMX_DBG(prm, bits) (false)
+#endif
+// host side: value of an experiment environment variable (0 in the default build)
+inline int experiment_env(const char* name) {
+#ifdef NMX_EXPERIMENTS
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -77,6 +97,16 @@ __device__ __forceinline__ double warp_scan_incl_f64(double v, int lane) {
     if (lane >= o) v += t;
   }
   return v;
+}
+
+// true exactly once per device and call site: function attributes (dynamic shared-memory size) are per DEVICE, so a
+// per-process flag would leave the kernels of a second GPU in the same process unconfigured
+inline bool once_per_device(bool (&done)[64]) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
 }
 
 inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {

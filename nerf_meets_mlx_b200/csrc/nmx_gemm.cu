@@ -580,13 +580,13 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   prof_begin(0, 2.0 * (double)g.M * g.N * (g.a0_k + a.a1_k), stream);
   if (g.N > 128) {
     using L = GemmSmem<256, 3>;
-    static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    static bool attr[64] = {};
+    if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); }
     gemm_kmajor_kernel<256, 3><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, tD, tM, a);
   } else {
     using L = GemmSmem<128, 4>;
-    static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    static bool attr[64] = {};
+    if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); }
     gemm_kmajor_kernel<128, 4><<<grid, kThreads, L::kAlloc, stream>>>(tA0, tA1, tB, tD, tM, a);
   }
   prof_end(stream);
@@ -624,13 +624,13 @@ int launch_wgrad(const WgradDesc& g, cudaStream_t stream) {
   prof_begin(1, 2.0 * (double)g.P * g.M * (g.N + (dual ? 64 : 0)), stream);
   if (dual) {
     using L = WgradSmem<3, true>;
-    static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    static bool attr[64] = {};
+    if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); }
     wgrad_kernel<3, true><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, tX2, a);
   } else {
     using L = WgradSmem<4, false>;
-    static bool attr = false;
-    if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); attr = true; }
+    static bool attr[64] = {};
+    if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(wgrad_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc)); }
     wgrad_kernel<4, false><<<dim3(splits, m_tiles), kThreads, L::kAlloc, stream>>>(tDY, tX, tX2, a);
   }
   prof_end(stream);

@@ -368,40 +368,66 @@ head_bwd_kernel(const bf16* __restrict__ h, int ldh, const float* __restrict__ W
 //   dW_feat[j, k] = sum_o Wd[o,j] G[o,k]                        (= d_feature^T h,    d_feature = d_hd Wd[:, :W])
 //   db_feat[j]    = sum_o db_dir[o] Wd[o,j]
 // with the bf16-rounded weights the tensor-core layers used.  Neither `feature` nor `d_feature` has to be kept in HBM.
+// 32 x 32 output tiles, K staged through shared memory in chunks of 32 (two tiny fp32 GEMMs of 8.4 MFLOP each: the first
+// version -- one block per output row with 256-iteration dependent loops -- took 30 us per pass, a fixed cost that is
+// 3 % of a 1024-ray shard's step).  Blocks [0, tilesA): dW_dir tiles; the rest: dW_feat tiles (+ db_feat on k-tile 0).
 __global__ void __launch_bounds__(256)
 fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__ db_dir, const float* __restrict__ Wf,
                           const float* __restrict__ bf, const float* __restrict__ Wd, int ldwd, int W, int Wh,
                           float* __restrict__ dWd, float* __restrict__ dWf, float* __restrict__ dbf) {
-  extern __shared__ float sh[];  // W floats
-  const int t = threadIdx.x;
-  if ((int)blockIdx.x < Wh) {  // one dir-layer output row o: dW_dir[o, 0:W]
-    const int o = blockIdx.x;
-    for (int k = t; k < W; k += blockDim.x) sh[k] = G[(size_t)o * W + k];
-    __syncthreads();
-    // a warp per output column j: lanes stride the contraction index, so the Wf row is read coalesced
-    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
-    for (int j = warp; j < W; j += nw) {
-      float acc = 0.0f;
-      const float* w = Wf + (size_t)j * W;
-      for (int k = lane; k < W; k += 32) acc += sh[k] * __bfloat162float(__float2bfloat16_rn(w[k]));
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 x 32 threads, 4 outputs each
+  const int tiles_j = W / 32;
+  const int tilesA = (Wh / 32) * tiles_j;
+  auto bfr = [](float v) { return __bfloat162float(__float2bfloat16_rn(v)); };
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if ((int)blockIdx.x < tilesA) {  // dW_dir[o, j] += sum_k G[o,k] bf16(Wf[j,k]) + db_dir[o] bf[j]
+    const int o0 = ((int)blockIdx.x / tiles_j) * 32, j0 = ((int)blockIdx.x % tiles_j) * 32;
+    for (int k0 = 0; k0 < W; k0 += 32) {
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
-      if (lane == 0) dWd[(size_t)o * ldwd + j] += acc + db_dir[o] * bf[j];
+      for (int i = 0; i < 4; ++i) {
+        sa[ty * 4 + i][tx] = G[(size_t)(o0 + ty * 4 + i) * W + k0 + tx];
+        sb[ty * 4 + i][tx] = bfr(Wf[(size_t)(j0 + ty * 4 + i) * W + k0 + tx]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        const float w = sb[tx][kk];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += sa[ty * 4 + i][kk] * w;
+      }
+      __syncthreads();
     }
-  } else {  // one feature-layer output row j: dW_feat[j, 0:W], db_feat[j]
-    const int j = blockIdx.x - Wh;
-    for (int o = t; o < Wh; o += blockDim.x) sh[o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldwd + j]));
-    __syncthreads();
-    for (int k = t; k < W; k += blockDim.x) {
-      float acc = 0.0f;
-      for (int o = 0; o < Wh; ++o) acc += sh[o] * G[(size_t)o * W + k];
-      dWf[(size_t)j * W + k] += acc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = o0 + ty * 4 + i, j = j0 + tx;
+      dWd[(size_t)o * ldwd + j] += acc[i] + db_dir[o] * bf[j];
     }
-    if (t == 0) {
-      float acc = 0.0f;
-      for (int o = 0; o < Wh; ++o) acc += db_dir[o] * sh[o];
-      dbf[j] += acc;
+  } else {  // dW_feat[j, k] += sum_o bf16(Wd[o,j]) G[o,k];  db_feat[j] += sum_o db_dir[o] bf16(Wd[o,j])
+    const int t = (int)blockIdx.x - tilesA;
+    const int j0 = (t / tiles_j) * 32, k0 = (t % tiles_j) * 32;
+    float accb = 0.0f;
+    for (int o0 = 0; o0 < Wh; o0 += 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sa[ty * 4 + i][tx] = bfr(Wd[(size_t)(o0 + ty * 4 + i) * ldwd + j0 + tx]);
+        sb[ty * 4 + i][tx] = G[(size_t)(o0 + ty * 4 + i) * W + k0 + tx];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int oo = 0; oo < 32; ++oo) {
+        const float g = sb[oo][tx];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += sa[oo][ty * 4 + i] * g;
+      }
+      if (k0 == 0 && ty == 0) {
+        for (int oo = 0; oo < 32; ++oo) accb += db_dir[o0 + oo] * sa[oo][tx];
+      }
+      __syncthreads();
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dWf[(size_t)(j0 + ty * 4 + i) * W + k0 + tx] += acc[i];
+    if (k0 == 0 && ty == 0) dbf[j0 + tx] += accb;
   }
 }
 
@@ -776,7 +802,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   prm.pos_prefetch_layer = prm.pos_last_layer + 2 < nl ? prm.pos_last_layer + 2 : nl - 1;
   {
     static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
+    if (dbg < 0) dbg = experiment_env("NMX_CHAIN_DBG");
     prm.dbg = dbg;
   }
   prm.bits = (c.training && chain_bwd_eligible(p)) ? (uint32_t*)(c.act + c.al.bits) : nullptr;
@@ -788,7 +814,7 @@ int forward_chain(const Ctx& c, int64_t npts, int64_t cap, float* out, int out_c
   if ((rc = make_tmap_bf16_2d(&maps.x0, c.X0(), npts, p->x0_cols, p->x0_cols, 128))) return rc;
   if (c.training) {
     prm.cap = (int)cap;
-    if (prm.dbg & 32) {
+    if (NMX_DBG(prm, 32)) {
       if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap * 4, 64, 64, 128))) return rc;
     } else if ((rc = make_tmap_bf16_2d(&maps.save, c.act + c.al.h0, (uint64_t)(D + 1) * cap, W, W, 128))) return rc;
     if (p->cfg.use_viewdirs) {
@@ -856,7 +882,7 @@ int backward_chain(const Ctx& c, int64_t row0, int64_t P, int64_t cap, const flo
   prm.max_ctas = max_ctas;
   {
     static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("NMX_CHAIN_DBG"); dbg = e ? atoi(e) : 0; }
+    if (dbg < 0) dbg = experiment_env("NMX_CHAIN_DBG");
     prm.dbg = dbg & ~3;  // bits 2 (trace), 3 (no mask reads), 4 (no dY stores) apply to the backward chain
   }
   if ((rc = make_tmap_bf16_2d(&maps.save, c.G(0) + row0 * W, (uint64_t)(D + 1) * cap - row0, W, W, 128))) return rc;
@@ -1015,7 +1041,8 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
   const int skip_l = p->cfg.skip_layer >= 0 ? p->cfg.skip_layer + 1 : -1;  // the layer whose input is [x_pos, h]
   if (d_input != nullptr && p->pos_pad > 256) { set_error("input gradient: encoded width <= 256"); return NMX_E_UNSUPPORTED; }
 
-  if (getenv("NMX_DEBUG_SYNC")) {
+  static const bool dbg_sync = getenv("NMX_DEBUG_SYNC") != nullptr;
+  if (dbg_sync) {
     cudaError_t e0 = cudaDeviceSynchronize();
     fprintf(stderr, "[nmx] bwd entry sync: %s | ws=%p act=%p params=%p d_out=%p d_params=%p P=%lld HD=%p GHD=%p hl=%p\n",
             cudaGetErrorString(e0), (void*)c.ws, (void*)c.act, (const void*)params, (const void*)d_out, (void*)d_params,
@@ -1027,22 +1054,27 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
     // wgrad(k) on a second stream, on its own share of the SMs, while the chain works on chunk k+1.  Measured on B200
     // this mixing does NOT pay (K=4: 7.4 ms vs 6.1 ms for the fine pass: per-SM bandwidth, 4x the wgrad flushes), so
     // the default is the sequential schedule K = 1; the path is kept for experiments.
-    static cudaStream_t s2 = nullptr;
-    static std::vector<cudaEvent_t> evs;
+    static cudaStream_t s2_dev[64] = {};  // second stream of the chunked experiment, one per device, created on demand
+    static std::vector<cudaEvent_t> evs_dev[64];
     static int n_chunks_cfg = -1, chain_sms_cfg = -1;
-    if (s2 == nullptr) {
-      NMX_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    if (n_chunks_cfg < 0) {
       const char* e1 = getenv("NMX_BWD_CHUNKS");
       const char* e2 = getenv("NMX_BWD_CHAIN_SMS");
-      n_chunks_cfg = e1 ? atoi(e1) : 1;
       chain_sms_cfg = e2 ? atoi(e2) : 96;
-      if (n_chunks_cfg < 1) n_chunks_cfg = 1;
       if (chain_sms_cfg < 8 || chain_sms_cfg > kNumSMs - 8) chain_sms_cfg = 96;
+      n_chunks_cfg = e1 ? atoi(e1) : 1;
+      if (n_chunks_cfg < 1) n_chunks_cfg = 1;
     }
+    int dev_id = 0;
+    NMX_CUDA(cudaGetDevice(&dev_id));
+    if (dev_id < 0 || dev_id >= 64) dev_id = 0;
+    if (n_chunks_cfg > 1 && s2_dev[dev_id] == nullptr) NMX_CUDA(cudaStreamCreateWithFlags(&s2_dev[dev_id], cudaStreamNonBlocking));
+    cudaStream_t s2 = s2_dev[dev_id];
+    std::vector<cudaEvent_t>& evs = evs_dev[dev_id];
     const int64_t tiles = (P + 127) / 128;
     int K = n_chunks_cfg;
     if (tiles < (int64_t)4 * kNumSMs * K) K = (int)(tiles / (4 * kNumSMs)) > 0 ? (int)(tiles / (4 * kNumSMs)) : 1;
-    while ((int)evs.size() < K + 2) {
+    while (K > 1 && (int)evs.size() < K + 2) {
       cudaEvent_t e;
       NMX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       evs.push_back(e);
@@ -1177,7 +1209,7 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
     }
     {  // feature / dir-layer weight gradients from G (after every chunk's wgrad has been accumulated)
       cudaStream_t sw = K > 1 ? s2 : s;
-      fold_feature_grads_kernel<<<W / 2 + W, 256, W * sizeof(float), sw>>>(
+      fold_feature_grads_kernel<<<(W / 64) * (W / 32) + (W / 32) * (W / 32), 256, 0, sw>>>(
           (const float*)(c.act + c.al.gfold), d_params + p->dir.b_off, params + p->feat.w_off, params + p->feat.b_off,
           params + p->dir.w_off, p->dir.in, W, W / 2, d_params + p->dir.w_off, d_params + p->feat.w_off,
           d_params + p->feat.b_off);

@@ -157,11 +157,11 @@ extern "C" int nmx_gemm_pair_bf16(const void* A, const void* Bm, float* D, int64
   if ((rc = make_tmap_bf16_2d(&tB, Bm, 256, (uint64_t)K, (uint64_t)K, 128))) return rc;
   PairArgs a;
   a.M = (int)M; a.K = K; a.D = D; a.ldd = 256;
-  a.no_store = getenv("NMX_PAIR_NOSTORE") ? 1 : 0;
-  a.b_only = getenv("NMX_PAIR_BONLY") ? 1 : 0;
+  a.no_store = experiment_env("NMX_PAIR_NOSTORE") ? 1 : 0;
+  a.b_only = experiment_env("NMX_PAIR_BONLY") ? 1 : 0;
   const int smem = kStages * kStageBytes + 256 + 1024;
-  static bool attr = false;
-  if (!attr) { NMX_CUDA(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  static bool attr[64] = {};
+  if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); }
   int tiles = (int)((M + 255) / 256);
   int pairs = kNumSMs / 2;
   if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;

@@ -255,8 +255,8 @@ int launch_wgrad_batch(const WgradBatchDesc& d, cudaStream_t stream) {
     o.cta0 = total;
     total += o.n_ctas;
   }
-  static bool attr = false;
-  if (!attr) { NMX_CUDA(cudaFuncSetAttribute(wgrad_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc)); attr = true; }
+  static bool attr[64] = {};
+  if (once_per_device(attr)) { NMX_CUDA(cudaFuncSetAttribute(wgrad_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAlloc)); }
   double flops = 0.0;
   for (int j = 0; j < d.n_jobs; ++j) flops += 2.0 * (double)d.P * d.job[j].M * (d.job[j].N + (d.job[j].x2_t >= 0 ? 64 : 0));
   prof_begin(1, flops, stream);

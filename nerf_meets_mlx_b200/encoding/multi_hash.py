@@ -5,22 +5,8 @@ import math
 import torch
 
 from .. import ops
+from ..ops import library as _library  # noqa: F401  (registers torch.ops.nmx.*)
 from . import Encoding
-
-
-class _HashGridFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, tables, x, scaled_res, log2_T):
-        ctx.save_for_backward(x, scaled_res)
-        ctx.shape = tables.shape
-        ctx.log2_T = log2_T
-        return ops.hashgrid_fwd(x, tables, scaled_res, log2_T)
-
-    @staticmethod
-    def backward(ctx, d_out):
-        x, scaled_res = ctx.saved_tensors
-        L, T, F = ctx.shape
-        return ops.hashgrid_bwd(x, scaled_res, d_out.contiguous(), L, F, ctx.log2_T), None, None, None
 
 
 class MultiHashEncoding(Encoding):
@@ -64,4 +50,5 @@ class MultiHashEncoding(Encoding):
 
     def forward(self, in_array):
         x = in_array.to(torch.float32).reshape(-1, 3).contiguous()
-        return _HashGridFunction.apply(self.hash_table, x, self.scaled_res, self.log2_hashmap_size)
+        # custom operator torch.ops.nmx.hashgrid_fwd; its backward (table scatter) is torch.ops.nmx.hashgrid_bwd
+        return torch.ops.nmx.hashgrid_fwd(x, self.hash_table, self.scaled_res, self.log2_hashmap_size)

@@ -4,33 +4,9 @@ Execution flow (as the reference): render -> batchify_rays -> render_rays[_eval]
 import torch
 
 from .. import ops, sampling
+from ..ops import library as _library  # noqa: F401  (registers torch.ops.nmx.*)
 from ..sampling import uniform, linear_disparity
 from . import ray
-
-
-class _CompositeFunction(torch.autograd.Function):
-    """raw2outputs as one fused kernel each way (K4)."""
-
-    @staticmethod
-    def forward(ctx, raw, z_vals, rays_d, noise, raw_noise_std, white_bkgd):
-        rgb, disp, acc, weights, depth = ops.composite_fwd(raw, z_vals, rays_d, noise, raw_noise_std, white_bkgd)
-        ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else raw.new_empty(0))
-        ctx.cfg = (raw_noise_std, white_bkgd, noise is not None)
-        return rgb, disp, acc, weights, depth
-
-    @staticmethod
-    def backward(ctx, d_rgb, d_disp, d_acc, d_weights, d_depth):
-        raw, z_vals, rays_d, noise = ctx.saved_tensors
-        std, wb, has_noise = ctx.cfg
-        B, n = z_vals.shape
-
-        def opt(t):
-            return None if t is None else t.contiguous()
-        if d_rgb is None:
-            d_rgb = torch.zeros((B, 3), device=raw.device)
-        d_raw = ops.composite_bwd(raw, z_vals, rays_d, d_rgb.contiguous(), opt(d_disp), opt(d_acc), opt(d_depth),
-                                  opt(d_weights), noise if has_noise else None, std, wb)
-        return d_raw, None, None, None, None, None
 
 
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, noise=None):
@@ -44,8 +20,9 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=F
         noise = torch.randn(raw.shape[:-1], device=raw.device)  # render.py:41-43
     if raw_noise_std <= 0.0:
         noise = None
-    return _CompositeFunction.apply(raw[..., :4].contiguous() if raw.shape[-1] != 4 else raw, z_vals, rays_d, noise,
-                                    float(raw_noise_std), bool(white_bkgd))
+    # one fused kernel each way (K4), as the custom operator torch.ops.nmx.composite_fwd (backward: nmx.composite_bwd)
+    return torch.ops.nmx.composite_fwd(raw[..., :4].contiguous() if raw.shape[-1] != 4 else raw, z_vals, rays_d, noise,
+                                       float(raw_noise_std), bool(white_bkgd))
 
 
 def decompose_ray_batch(rays_batch_linear, is_time_included: bool = False):

@@ -134,3 +134,35 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_custom_ops_registered_with_fake_kernels():
+    """torch.ops.nmx.* exist (north_star: "PyTorch custom ops over a thin C-ABI layer") and their fake kernels propagate
+    shapes / dtypes without running CUDA code (FakeTensorMode builds fake cuda tensors on this GPU-less host)."""
+    import torch
+    from torch._subclasses import FakeTensorMode
+    from nerf_meets_mlx_b200.ops import library as lib
+    for name in lib.ALL_OPS:
+        assert hasattr(torch.ops.nmx, name), name
+    B, n, N = 7, 64, 128
+    with FakeTensorMode():
+        c = lambda *s: torch.empty(*s, device="cuda")
+        z = torch.ops.nmx.sample_z(c(B), c(B), n)
+        assert z.shape == (B, n) and z.device.type == "cuda"
+        rgb, disp, acc, w, depth = torch.ops.nmx.composite_fwd(c(B, n, 4), z, c(B, 3))
+        assert rgb.shape == (B, 3) and w.shape == (B, n, 1) and depth.shape == (B, 1)
+        assert torch.ops.nmx.composite_bwd(c(B, n, 4), z, c(B, 3), rgb).shape == (B, n, 4)
+        zi, zm = torch.ops.nmx.sample_pdf(z, w, c(B, N))
+        assert zi.shape == (B, N) and zm.shape == (B, n + N)
+        assert torch.ops.nmx.pe_embedder(c(5, 3), 10).shape == (5, 63)
+        assert torch.ops.nmx.pe_sinusoidal(c(5, 2), c(10)).shape == (5, 40)
+        assert torch.ops.nmx.sh_encode(c(5, 3), 4).shape == (5, 25)
+        feat = torch.ops.nmx.hashgrid_fwd(c(9, 3), c(16, 1 << 10, 2), c(16), 10)
+        assert feat.shape == (9, 32)
+        assert torch.ops.nmx.hashgrid_bwd(c(9, 3), c(16), feat, 16, 2, 10).shape == (16, 1 << 10, 2)
+        assert torch.ops.nmx.assemble_rays(c(B, 3), c(B, 3), 2.0, 6.0).shape == (B, 11)
+        loss, d = torch.ops.nmx.mse_fwd_bwd(rgb, c(B, 3))
+        assert loss.shape == (1,) and d.shape == (B, 3)
+        out = torch.ops.nmx.mlp_fwd(0, c(1024, dtype=torch.uint8) if False else torch.empty(1024, dtype=torch.uint8, device="cuda"),
+                                    c(100), 1, c(B, 11), z, None, B, n, 4, False)
+        assert out.shape == (B * n, 4)

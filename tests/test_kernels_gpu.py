@@ -339,3 +339,34 @@ def test_metric_mirror(golden):
     np.testing.assert_allclose(float(metric.PSNR()(dev(g["pred"]), dev(g["gt"]))), float(g["psnr"]), rtol=2e-6)
     with pytest.raises(NotImplementedError):
         metric.SSIM()(dev(g["pred"]), dev(g["gt"]))
+
+
+# ------------------------------------------------------------------ torch.library custom operators
+def test_custom_ops_opcheck(ops):
+    """torch.library.opcheck: schema, fake kernel vs real kernel (shapes / dtypes / strides), autograd registration and
+    AOT dispatch of the custom operators the mirror API is built on."""
+    from torch.library import opcheck
+    from nerf_meets_mlx_b200.ops import library  # noqa: F401
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s: torch.rand(*s, device="cuda", generator=g)
+    B, n, N = 33, 64, 128
+    z = torch.sort(2.0 + 4.0 * r(B, n), dim=-1).values
+    raw = (r(B, n, 4) - 0.3).requires_grad_(True)
+    d = r(B, 3) - 0.5
+    opcheck(torch.ops.nmx.composite_fwd.default, (raw, z, d, None, 0.0, True))
+    opcheck(torch.ops.nmx.composite_bwd.default, (raw.detach(), z, d, r(B, 3)))
+    w = torch.ops.nmx.composite_fwd(raw.detach(), z, d)[3]
+    opcheck(torch.ops.nmx.sample_pdf.default, (z, w, r(B, N)))
+    opcheck(torch.ops.nmx.sample_z.default, (2.0 + r(B), 6.0 + r(B), n, False))
+    opcheck(torch.ops.nmx.pe_embedder.default, (r(50, 3), 10, True))
+    opcheck(torch.ops.nmx.sh_encode.default, (r(50, 3), 4))
+    tables = (r(4, 1 << 10, 2) - 0.5).requires_grad_(True)
+    res = torch.tensor([16.0, 32.0, 64.0, 128.0], device="cuda")
+    opcheck(torch.ops.nmx.hashgrid_fwd.default, (r(77, 3), tables, res, 10))
+    opcheck(torch.ops.nmx.assemble_rays.default, (r(B, 3), r(B, 3) + 0.1, 2.0, 6.0))
+    opcheck(torch.ops.nmx.mse_fwd_bwd.default, (r(B, 3), r(B, 3)))
+    # autograd through the custom operators == the explicit backward kernels
+    rgb, disp, acc, wts, depth = torch.ops.nmx.composite_fwd(raw, z, d, None, 0.0, False)
+    (rgb.sum() + 0.5 * acc.sum()).backward()
+    want = ops.composite_bwd(raw.detach(), z, d, torch.ones(B, 3, device="cuda"), d_acc=torch.full((B, 1), 0.5, device="cuda"))
+    np.testing.assert_array_equal(raw.grad.cpu().numpy(), want.cpu().numpy())
