@@ -88,4 +88,40 @@ struct Chain2Launch {
 };
 int launch_chain2(const Chain2Launch& a, cudaStream_t stream);
 
+// Training forward of the same net on CTA pairs (nmx_chain2t.cu): saves h_0 .. h_7, hd, the ReLU sign bits and the
+// encoded input tile X0, in the layouts the one-tile training chain (nmx_chain.cu) writes.
+struct Chain2TrainLaunch {
+  long long P;                 // points (all rays of the pass: p0 = 0)
+  const float* params;
+  float* out;                  // [P, 4] fp32
+  const void* w_ptr[10];
+  int w_k[10];
+  int bias_off[10];
+  int alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off;
+  const float* rays; int ray_stride; const float* z;
+  int n_per_ray; int in_dir;   // in_dir = encoded view-dir channels (27)
+  int dir_w_off, dir_ldw;
+  const void* dir_pe;          // [rays, 64] bf16 per-ray view-dir PE (encode_dirs_kernel)
+  float* scratch;              // chain2_train_scratch_bytes(rays): constants block + per-ray dir-layer term
+  void* save_base; long long save_rows; long long cap;  // activation store [(D + 1) * cap, 256] bf16
+  void* hd;                    // [P, 128] bf16
+  void* x0;                    // [P, 128] bf16
+  uint32_t* bits;              // sign-bit store [(D + 1) * cap][8] uint32
+};
+// Backward data-gradient chain on CTA pairs (nmx_chain2t.cu): layer order d_feature, dY_7, dY_6 .. dY_0.
+struct Chain2BwdLaunch {
+  long long P;
+  const float* params;         // packed fp32 parameters (w_alpha, w_rgb)
+  const float* d_out;          // [P, 4] fp32
+  const void* w_ptr[9];        // transposed bf16 weights [256, K]: W_dir[:, :W]^T (K = 128), W_feat^T, W_7^T .. W_1^T (h parts)
+  int w_k[9];
+  int alpha_w_off, rgb_w_off;
+  const uint32_t* bits;        // the forward's sign-bit store
+  void* save_base; long long save_rows; long long cap;  // dY store [(D + 1) * cap, 256]
+  void* ghd;                   // d_hd [P, 128]
+};
+int launch_chain2_bwd(const Chain2BwdLaunch& a, cudaStream_t stream);
+int64_t chain2_train_scratch_bytes(int64_t n_rays);
+int launch_chain2_train(const Chain2TrainLaunch& a, cudaStream_t stream);
+
 }  // namespace nmx

@@ -918,6 +918,40 @@ int forward_chain2(const Ctx& c, int64_t npts, float* out, const EncIn& enc) {
   return launch_chain2(a, c.s);
 }
 
+// Training forward on CTA pairs (nmx_chain2t.cu): same net as chain2_ok, saved tensors in the one-tile chain's layouts.
+// NMX_DISABLE_CHAIN2T=1 falls back to the one-tile training chain.
+bool chain2t_ok(const nmx_mlp_plan* p, int enc_kind, int n, int64_t P) {
+  static int off = -1;
+  if (off < 0) off = getenv("NMX_DISABLE_CHAIN2T") ? 1 : 0;
+  return !off && chain2_ok(p, enc_kind, n) && chain_bwd_eligible(p) && P >= 4096;
+}
+
+int forward_chain2_train(const Ctx& c, int64_t P, float* out, const EncIn& enc) {
+  const nmx_mlp_plan* p = c.p;
+  Chain2TrainLaunch a;
+  memset(&a, 0, sizeof(a));
+  a.P = P; a.params = c.params; a.out = out;
+  for (int l = 0; l < 8; ++l) {
+    a.w_ptr[l] = c.ws + p->wf_off[l]; a.w_k[l] = p->wf_k[l]; a.bias_off[l] = (int)p->trunk[l].b_off;
+  }
+  a.w_ptr[8] = c.ws + p->wf_feat; a.w_k[8] = p->W; a.bias_off[8] = (int)p->feat.b_off;
+  a.w_ptr[9] = c.ws + p->wf_dir; a.w_k[9] = p->wf_dir_k; a.bias_off[9] = (int)p->dir.b_off;
+  a.alpha_w_off = (int)p->alpha.w_off; a.alpha_b_off = (int)p->alpha.b_off;
+  a.rgb_w_off = (int)p->rgb.w_off; a.rgb_b_off = (int)p->rgb.b_off;
+  a.rays = enc.rays; a.ray_stride = enc.ray_stride; a.z = enc.z; a.n_per_ray = enc.n; a.in_dir = p->in_dir;
+  a.dir_w_off = (int)p->dir.w_off; a.dir_ldw = p->dir.in;
+  // per-ray scratch inside the dirpe_bytes region: [PE(dir) table: rays x 128 B | constants + dir-layer term: 512 B / ray]
+  const int64_t n_rays = (P + enc.n - 1) / enc.n;
+  uint8_t* base = c.ws + p->weights_bytes;
+  a.dir_pe = base;
+  const int64_t off = align256(n_rays * 128);
+  if (off + chain2_train_scratch_bytes(n_rays) > dirpe_bytes(p)) { set_error("chain2 train: per-ray scratch does not fit"); return NMX_E_BADARG; }
+  a.scratch = (float*)(base + off);
+  a.save_base = c.act + c.al.h0; a.save_rows = (int64_t)(p->D + 1) * p->max_points; a.cap = p->max_points;
+  a.hd = c.HD(); a.x0 = c.X0(); a.bits = (uint32_t*)(c.act + c.al.bits);
+  return launch_chain2_train(a, c.s);
+}
+
 }  // namespace
 
 extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
@@ -945,6 +979,7 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
     if (chain_eligible(p)) {
       EncIn ei{x_or_rays, ray_stride, z, 0, n};
+      if (chain2t_ok(p, enc_kind, n, P)) return forward_chain2_train(c, P, out, ei);
       return forward_chain(c, P, p->max_points, out, out_cols, &ei);
     }
     return forward_chunk(c, P, out, out_cols);
@@ -1095,7 +1130,22 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
       if (rows <= 0) break;
       const bool alone_chain = (K == 1 || k == 0);            // nothing to overlap with yet: use every SM
       const bool alone_wgrad = (K == 1 || k == K - 1);        // last chunk: the chain is finished
-      if ((rc = backward_chain(c, r0, rows, p->max_points, d_out, alone_chain ? 0 : chain_sms_cfg, s))) return rc;
+      static int pair_bwd_off = -1;
+      if (pair_bwd_off < 0) pair_bwd_off = getenv("NMX_DISABLE_CHAIN2B") ? 1 : 0;
+      if (K == 1 && !pair_bwd_off && chain2_ok(p, 1, 8) && P >= 4096) {
+        // the whole pass on CTA pairs, two tiles in ping-pong (nmx_chain2t.cu)
+        Chain2BwdLaunch a;
+        memset(&a, 0, sizeof(a));
+        a.P = P; a.params = params; a.d_out = d_out;
+        a.w_ptr[0] = c.ws + p->wt_dir; a.w_k[0] = W / 2;
+        a.w_ptr[1] = c.ws + p->wt_feat; a.w_k[1] = W;
+        for (int l = p->D - 1; l >= 1; --l) { a.w_ptr[2 + (p->D - 1 - l)] = c.ws + p->wt_off[l]; a.w_k[2 + (p->D - 1 - l)] = W; }
+        a.alpha_w_off = (int)p->alpha.w_off; a.rgb_w_off = (int)p->rgb.w_off;
+        a.bits = (const uint32_t*)(c.act + c.al.bits);
+        a.save_base = c.G(0); a.save_rows = (int64_t)(p->D + 1) * p->max_points; a.cap = p->max_points;
+        a.ghd = c.GHD();
+        if ((rc = launch_chain2_bwd(a, s))) return rc;
+      } else if ((rc = backward_chain(c, r0, rows, p->max_points, d_out, alone_chain ? 0 : chain_sms_cfg, s))) return rc;
       cudaStream_t sw = K > 1 ? s2 : s;
       if (K > 1) {
         NMX_CUDA(cudaEventRecord(evs[k], s));
