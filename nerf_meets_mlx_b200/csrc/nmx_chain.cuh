@@ -117,6 +117,7 @@ struct Chain2BwdLaunch {
   int w_k[9];
   int alpha_w_off, rgb_w_off;
   const uint32_t* bits;        // the forward's sign-bit store
+  int bits_word_major;         // 1: 4 KB tiles are [8 words][128 rows] (written by the pair forward), 0: [128 rows][8 words]
   void* save_base; long long save_rows; long long cap;  // dY store [(D + 1) * cap, 256]
   void* ghd;                   // d_hd [P, 128]
 };

@@ -421,7 +421,9 @@ mlp_chain2_train_kernel(const __grid_constant__ Maps maps, const Params prm) {
           const int tile = tx + t * num_clusters;
           const long long row = (long long)tile * 256 + (long long)rank * 128 + row_local;
           const uint32_t act_row_addr = act_base + (uint32_t)(t * 5 * kChunk) + (uint32_t)row_local * 128u;
-          const uint32_t bits_row = smem_u32(smem + SmemT::kBitsOff + t * kBitsTile) + (uint32_t)row_local * 32u;
+          // sign-bit staging tile, WORD-major [8 words][128 rows]: a warp's 32 rows write 32 consecutive words (the
+          // row-major layout of the one-tile chain is an 8-way bank conflict per store)
+          const uint32_t bits_row = smem_u32(smem + SmemT::kBitsOff + t * kBitsTile) + (uint32_t)row_local * 4u;
           const uint32_t tacc = tmem_base + (uint32_t)t * 256u + ((uint32_t)(q * 32) << 16);
           float a0 = 0.0f;
           float rgbp[3] = {0.0f, 0.0f, 0.0f};
@@ -445,7 +447,7 @@ mlp_chain2_train_kernel(const __grid_constant__ Maps maps, const Params prm) {
           for (int h = 0; h < nh; ++h) {
             const int c = 2 * h + (part >> 1);
             const int c0 = c * 64 + sub * 32;
-            const uint32_t bits_addr = bits_row + (uint32_t)(4 * h + part) * 4u;
+            const uint32_t bits_addr = bits_row + (uint32_t)(4 * h + part) * 512u;
             tmem_ld_wait_regs<32>(r32);
             if (h == nh - 1) {
               tc_fence_before();
@@ -574,6 +576,7 @@ struct ParamsB {
   const uint32_t* bits;      // sign-bit store [(D + 1) * cap rows][8]
   int cap;
   int alpha_w_off, rgb_w_off;
+  int bits_wm;               // sign-bit tiles are word-major [8][128] (pair forward) instead of row-major [128][8]
 };
 struct MapsB {
   CUtensorMap w[kNB];        // transposed bf16 weights [256, K_b], box 128 x 64
@@ -843,7 +846,8 @@ mlp_chain2_bwd_kernel(const __grid_constant__ MapsB maps, const ParamsB prm) {
       mbar_wait(&bits_full[t * 2 + buf], (mstep[t] >> 1) & 1u);
       uint32_t v;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v)
-                   : "r"(smem_u32(smem + SmemB::kBitsOff + (t * 2 + buf) * kBitsTile) + (uint32_t)row_local * 32u + (uint32_t)w * 4u)
+                   : "r"(smem_u32(smem + SmemB::kBitsOff + (t * 2 + buf) * kBitsTile) +
+                         (prm.bits_wm ? (uint32_t)w * 512u + (uint32_t)row_local * 4u : (uint32_t)row_local * 32u + (uint32_t)w * 4u))
                    : "memory");
       return v;
     };
@@ -1039,7 +1043,7 @@ int launch_chain2_bwd(const Chain2BwdLaunch& a, cudaStream_t stream) {
   if ((rc = make_tmap_bf16_2d(&maps.save, a.save_base, (uint64_t)a.save_rows, 256, 256, 128))) return rc;
   if ((rc = make_tmap_bf16_2d(&maps.hd, a.ghd, (uint64_t)a.P, 128, 128, 128))) return rc;
   prm.P = (int)a.P; prm.params = a.params; prm.d_out = a.d_out; prm.bits = a.bits; prm.cap = (int)a.cap;
-  prm.alpha_w_off = a.alpha_w_off; prm.rgb_w_off = a.rgb_w_off;
+  prm.alpha_w_off = a.alpha_w_off; prm.rgb_w_off = a.rgb_w_off; prm.bits_wm = a.bits_word_major;
   static bool attr[64] = {};
   if (once_per_device(attr))
     NMX_CUDA(cudaFuncSetAttribute(mlp_chain2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemB::kAlloc));

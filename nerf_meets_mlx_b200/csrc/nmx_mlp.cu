@@ -48,6 +48,7 @@ struct nmx_mlp_plan {
   int64_t weights_bytes;
   // activation region (offsets relative to its start; depend on capacity)
   int64_t act_points_train, act_points_infer;
+  int bits_word_major;  // layout of the sign-bit tiles written by the last saving forward (1 = pair kernel, word-major)
 };
 
 namespace {
@@ -979,7 +980,8 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
     if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
     if (chain_eligible(p)) {
       EncIn ei{x_or_rays, ray_stride, z, 0, n};
-      if (chain2t_ok(p, enc_kind, n, P)) return forward_chain2_train(c, P, out, ei);
+      p->bits_word_major = chain2t_ok(p, enc_kind, n, P) ? 1 : 0;
+      if (p->bits_word_major) return forward_chain2_train(c, P, out, ei);
       return forward_chain(c, P, p->max_points, out, out_cols, &ei);
     }
     return forward_chunk(c, P, out, out_cols);
@@ -1141,11 +1143,14 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
         a.w_ptr[1] = c.ws + p->wt_feat; a.w_k[1] = W;
         for (int l = p->D - 1; l >= 1; --l) { a.w_ptr[2 + (p->D - 1 - l)] = c.ws + p->wt_off[l]; a.w_k[2 + (p->D - 1 - l)] = W; }
         a.alpha_w_off = (int)p->alpha.w_off; a.rgb_w_off = (int)p->rgb.w_off;
-        a.bits = (const uint32_t*)(c.act + c.al.bits);
+        a.bits = (const uint32_t*)(c.act + c.al.bits); a.bits_word_major = p->bits_word_major;
         a.save_base = c.G(0); a.save_rows = (int64_t)(p->D + 1) * p->max_points; a.cap = p->max_points;
         a.ghd = c.GHD();
         if ((rc = launch_chain2_bwd(a, s))) return rc;
-      } else if ((rc = backward_chain(c, r0, rows, p->max_points, d_out, alone_chain ? 0 : chain_sms_cfg, s))) return rc;
+      } else {
+        if (p->bits_word_major) { set_error("nmx_mlp_bwd: the forward ran on CTA pairs (word-major sign bits); the pair backward is disabled or ineligible"); return NMX_E_UNSUPPORTED; }
+        if ((rc = backward_chain(c, r0, rows, p->max_points, d_out, alone_chain ? 0 : chain_sms_cfg, s))) return rc;
+      }
       cudaStream_t sw = K > 1 ? s2 : s;
       if (K > 1) {
         NMX_CUDA(cudaEventRecord(evs[k], s));

@@ -243,6 +243,8 @@ class NeRF(torch.nn.Module):
             raise ValueError(f"expected last dim {expect}, got {x.shape[-1]}")
         P = x.numel() // expect
         x2 = x.reshape(P, expect)
+        if not torch.is_grad_enabled():  # inference: nothing is saved (ctx.needs_input_grad is not reliable under no_grad)
+            return self._fwd_raw(0, x2, None, None, P, 1, save=False).reshape(*x.shape[:-1], self.out_cols)
         rows = self.max_save_points
         if torch.is_grad_enabled() and (self.flat.requires_grad or x2.requires_grad) and P > rows:
             out = torch.cat([_MLPFunction.apply(self.flat, self, 0, x2[i:i + rows], None, None, min(rows, P - i), 1)
@@ -256,6 +258,8 @@ class NeRF(torch.nn.Module):
         rays = rays.float().contiguous()
         z_vals = z_vals.float().contiguous()
         B, n = z_vals.shape
+        if not torch.is_grad_enabled():
+            return self._fwd_raw(1, rays, z_vals, None, B, n, save=False).reshape(B, n, self.out_cols)
         rows = max(1, self.max_save_points // n)
         if torch.is_grad_enabled() and self.flat.requires_grad and B > rows:
             # a differentiable pass keeps ~10 KB of activations per point: bound the workspace by running ray chunks as
@@ -270,7 +274,10 @@ class NeRF(torch.nn.Module):
         """Fused path for the image demo: SinusoidalEncoding generated in the operand producer from raw coords."""
         x = x.float().contiguous()
         P = x.shape[0]
-        return _MLPFunction.apply(self.flat, self, 2, x, None, bands.float().contiguous(), P, 1)
+        bands = bands.float().contiguous()
+        if not torch.is_grad_enabled():
+            return self._fwd_raw(2, x, None, bands, P, 1, save=False)
+        return _MLPFunction.apply(self.flat, self, 2, x, None, bands, P, 1)
 
     def __del__(self):
         try:

@@ -45,7 +45,11 @@ def view(off, rows, cols):
 saved = {"raw": raw.cpu(), "x0": view(x0, P, x0_cols).float().cpu(), "hd": view(hd, P, 128).float().cpu()}
 for l in range(8):
     saved[f"h{l}"] = view(h0 + l * hs, P, 256).float().cpu()
-b = ws[base + bits: base + bits + 9 * cap * 32].view(torch.int32).view(9, cap, 8)[:, :P].cpu().numpy().astype(np.uint32)
+b = ws[base + bits: base + bits + 9 * cap * 32].view(torch.int32).view(9, cap, 8)
+import os
+if P >= 4096 and not os.environ.get("NMX_DISABLE_CHAIN2T"):  # pair forward: each 4 KB tile is word-major [8][128]
+    b = b.reshape(9, cap // 128, 8, 128).permute(0, 1, 3, 2).reshape(9, cap, 8)
+b = b[:, :P].cpu().numpy().astype(np.uint32)
 # sign bits must describe the activations saved by the SAME run
 for slot in range(9):
     cols = 256 if slot < 8 else 128
