@@ -1086,11 +1086,9 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
             (long long)P, (void*)c.HD(), (void*)c.GHD(), (const void*)hl);
   }
   if (chain_bwd_eligible(p)) {
-    // The data-gradient chain is bound by HBM *writes* (every dY is kept for wgrad; pure writes peak at ~3.9 TB/s on
-    // B200) and the wgrad kernels by HBM *reads*.  NMX_BWD_CHUNKS=K > 1 cuts the pass into K point chunks and runs
-    // wgrad(k) on a second stream, on its own share of the SMs, while the chain works on chunk k+1.  Measured on B200
-    // this mixing does NOT pay (K=4: 7.4 ms vs 6.1 ms for the fine pass: per-SM bandwidth, 4x the wgrad flushes), so
-    // the default is the sequential schedule K = 1; the path is kept for experiments.
+    // NMX_BWD_CHUNKS=K > 1 (experiment) cuts the pass into K point chunks and runs wgrad(k) on a second stream, on its own
+    // share of the SMs, while the chain works on chunk k+1.  Measured on B200 this mixing does NOT pay (K=4: 7.4 ms vs
+    // 6.1 ms for the fine pass: per-SM bandwidth, 4x the wgrad flushes), so the default is the sequential schedule K = 1.
     static cudaStream_t s2_dev[64] = {};  // second stream of the chunked experiment, one per device, created on demand
     static std::vector<cudaEvent_t> evs_dev[64];
     static int n_chunks_cfg = -1, chain_sms_cfg = -1;

@@ -1,1 +1,1 @@
-from . import ray, render  # noqa: F401
+from . import ray, render, turntable  # noqa: F401

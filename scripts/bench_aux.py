@@ -116,7 +116,7 @@ def main():
     x = [rnd(P, 3) * 8 - 4 for _ in range(ns)]
     out = torch.empty(P, 63, device=dev)
     sec = timed(lambda i: L.call("nmx_pe_embedder_fwd", ptr(x[i]), ptr(out), i64(P), i32(3), i32(10), i32(1), stream()), ns)
-    report(rows, "pe_embedder 3->63", P, "points", 12 + 252, sec, "write-dominated (HBM write-only peak is ~3.9 TB/s)")
+    report(rows, "pe_embedder 3->63", P, "points", 12 + 252, sec, "write-dominated; sincosf-bound (write-only HBM peak is 6.3 TB/s, profiles/r2_bw_probe.txt)")
     out = torch.empty(P, 25, device=dev)
     sec = timed(lambda i: L.call("nmx_sh_encode_fwd", ptr(x[i]), i32(3), ptr(out), i64(P), i32(4), stream()), ns)
     report(rows, "sh_encode deg 4", P, "points", 12 + 100, sec, "write-dominated")

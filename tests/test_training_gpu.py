@@ -190,3 +190,25 @@ def test_train_iteration_from_pixels_matches_ray_inputs():
     # update whose weight gradients were reduced with fp32 atomics (order-dependent in the last bits)
     assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[1][0])
     assert abs(losses[0][1] - losses[1][1]) <= 1e-3 * abs(losses[1][1])
+
+
+def test_turntable_loop_matches_single_renders():
+    """render_turntable (__test_nerf.py:326-341) == rendering each pose of the loader's render_poses circle on its own."""
+    from nerf_meets_mlx_b200.models.NeRF import create_NeRF, default_args
+    from nerf_meets_mlx_b200.ops.pose import pose_spherical
+    from nerf_meets_mlx_b200.rendering import render as R
+    from nerf_meets_mlx_b200.rendering.turntable import render_turntable, to8b
+    kw_train, kw_test, _, _ = create_NeRF(default_args(N_importance=16, n_depth_samples=16))
+    H, W, focal = 10, 12, 15.0
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    poses = torch.stack([torch.as_tensor(np.asarray(pose_spherical(float(a), -30.0, 4.0), dtype=np.float32)) for a in (-180.0, -60.0, 60.0)])
+    u = torch.rand(H * W, 16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    kw = dict(kw_test, near=2.0, far=6.0, u_vals=u)
+    got = []
+    frames = render_turntable(H, W, K, poses, kw, writer=got.append)
+    assert frames.shape == (3, H, W, 3) and frames.dtype == np.uint8 and len(got) == 3
+    for i in range(3):
+        with torch.no_grad():
+            rgb = R.render(H, W, K, c2w=poses[i][:3, :4].cuda(), **kw)[0]
+        np.testing.assert_array_equal(frames[i], to8b(rgb))
+        np.testing.assert_array_equal(got[i], frames[i])
