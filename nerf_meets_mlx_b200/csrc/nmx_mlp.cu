@@ -196,19 +196,31 @@ __global__ void encode_dirs_kernel(const float* __restrict__ rays, int ray_strid
   }
 }
 
-// enc_kind 0: X0[p, :] = [x[p, 0:in_pos], 0-pad | x[p, in_pos:in_pos+in_dir], 0-pad]  (already-encoded fp32 input)
-__global__ void encode_copy_kernel(const float* __restrict__ x, bf16* __restrict__ x0, int64_t p0, int64_t npts,
-                                   int in_pos, int in_dir, int pos_pad, int dir_pad) {
+// enc_kind 0: X0[p, :] = [x[p, 0:in_pos], 0-pad | x[p, in_pos:in_pos+in_dir], 0-pad]  (already-encoded fp32 input).
+// One thread per 8 output columns: eight fp32 loads, one 16 B bf16 store.
+__global__ void __launch_bounds__(256)
+encode_copy_kernel(const float* __restrict__ x, bf16* __restrict__ x0, int64_t p0, int64_t npts, int in_pos, int in_dir,
+                   int pos_pad, int dir_pad) {
   const int cols = pos_pad + dir_pad;
+  const int groups = cols >> 3;
   const int in_tot = in_pos + in_dir;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts * cols;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t lp = t / cols;
-    int c = (int)(t - lp * cols);
-    float v = 0.0f;
-    if (c < in_pos) v = x[(p0 + lp) * in_tot + c];
-    else if (c >= pos_pad && c - pos_pad < in_dir) v = x[(p0 + lp) * in_tot + in_pos + (c - pos_pad)];
-    x0[t] = __float2bfloat16_rn(v);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts * groups; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t lp = t / groups;
+    const int c0 = (int)(t - lp * groups) << 3;
+    const float* row = x + (p0 + lp) * in_tot;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      v[e] = c < in_pos ? __ldg(row + c) : ((c >= pos_pad && c - pos_pad < in_dir) ? __ldg(row + in_pos + (c - pos_pad)) : 0.0f);
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(x0 + lp * cols + c0) = o;
   }
 }
 
@@ -235,7 +247,9 @@ __global__ void encode_sinusoidal_kernel(const float* __restrict__ x, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ small heads
-// out[p, col0 + o] = h[p, :] . Wt[o, :] + b[o],  o < n_out <= 8   (one warp per point, K <= 256, K % 64 == 0)
+// out[p, col0 + o] = h[p, :] . Wt[o, :] + b[o],  o < n_out <= 8.  Every lane loads 16 B (8 bf16 columns) of a point's row,
+// so a point takes K/8 lanes and a warp iteration covers 256/K points with one coalesced 512 B transaction (K = 64: four
+// points per warp instead of one with 24 idle lanes).  K in {64, 128, 256}.
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restrict__ Wt, const float* __restrict__ b,
                 int n_out, float* __restrict__ out, int ldo, int col0, int64_t P) {
@@ -243,14 +257,19 @@ head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
   for (int i = threadIdx.x; i < n_out * K; i += blockDim.x) s_w[i] = Wt[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int lpp = K >> 3;        // lanes per point
+  const int ppw = 32 / lpp;      // points per warp iteration
+  const int sub = lane / lpp, cl = lane - sub * lpp;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t p = warp0; p < P; p += nw) {
+  for (int64_t pb = warp0 * ppw; pb < P; pb += nw * ppw) {
+    const int64_t p = pb + sub;
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = 0.0f;
-    for (int k0 = lane * 8; k0 < K; k0 += 256) {  // one 16 B vector load per lane: a coalesced 2*K-byte row
-      uint4 raw = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + k0));
+    if (p < P) {
+      const int k0 = cl * 8;
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(h + p * ldh + k0));
       const bf16* hv = reinterpret_cast<const bf16*>(&raw);
       float hf[8];
 #pragma unroll
@@ -260,20 +279,24 @@ head_fwd_kernel(const bf16* __restrict__ h, int ldh, int K, const float* __restr
         if (o < n_out) {
           const float4 w0 = *reinterpret_cast<const float4*>(s_w + o * K + k0);
           const float4 w1 = *reinterpret_cast<const float4*>(s_w + o * K + k0 + 4);
-          acc[o] += hf[0] * w0.x + hf[1] * w0.y + hf[2] * w0.z + hf[3] * w0.w + hf[4] * w1.x + hf[5] * w1.y +
-                    hf[6] * w1.z + hf[7] * w1.w;
+          acc[o] = hf[0] * w0.x + hf[1] * w0.y + hf[2] * w0.z + hf[3] * w0.w + hf[4] * w1.x + hf[5] * w1.y + hf[6] * w1.z +
+                   hf[7] * w1.w;
         }
       }
     }
+    // sum over the lpp lanes of a point (lpp = 8, 16 or 32: xor offsets below lpp stay inside the group)
 #pragma unroll
-    for (int o = 0; o < 8; ++o)
-      if (o < n_out) acc[o] = warp_sum(acc[o]);
-    if (lane < n_out) {
+    for (int o = 0; o < 8; ++o) {
+      if (o < n_out) {
+        for (int off = lpp >> 1; off > 0; off >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+      }
+    }
+    if (p < P && cl < n_out) {
       float v = 0.0f;
 #pragma unroll
       for (int o = 0; o < 8; ++o)
-        if (o == lane) v = acc[o];
-      out[p * ldo + col0 + lane] = v + b[lane];
+        if (o == cl) v = acc[o];
+      out[p * ldo + col0 + cl] = v + b[cl];
     }
   }
 }
@@ -669,7 +692,7 @@ int encode_chunk(const Ctx& c, const float* x_or_rays, int ray_stride, const flo
     encode_sinusoidal_kernel<<<grid_for(npts * p->pos_pad, 256, 16), 256, 0, c.s>>>(
         x_or_rays, bands, c.X0(), p0, npts, in_dim, p->cfg.n_freqs_pos, p->pos_pad);
   } else {
-    encode_copy_kernel<<<grid_for(npts * p->x0_cols, 256, 16), 256, 0, c.s>>>(x_or_rays, c.X0(), p0, npts, p->in_pos,
+    encode_copy_kernel<<<grid_for(npts * (p->x0_cols / 8), 256, 16), 256, 0, c.s>>>(x_or_rays, c.X0(), p0, npts, p->in_pos,
                                                                             p->in_dir, p->pos_pad, p->dir_pad);
   }
   NMX_LAUNCH_CHECK();

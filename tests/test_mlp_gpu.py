@@ -1,6 +1,7 @@
 """NeRF MLP (bf16 tcgen05 GEMMs, fp32 accumulate) vs the fp32 oracle (torch-CPU restatement of NeRF.forward).
-north_star tolerance: 1e-2 relative for bf16 MLP outputs; gradients are held to 3e-2 normwise (bf16 activations
-and bf16 back-propagated signals)."""
+north_star tolerance: 1e-2 relative for bf16 MLP outputs.  Gradients: <= 1e-2 normwise against a reference that
+emulates the kernels' bf16 storage points; against the fp32 oracle the measured error is recorded per case (see
+GRAD_VS_FP32 below) -- the parity claim for gradients is the full-size test (tests/test_fullsize_gpu.py: <= 2.4e-2)."""
 import numpy as np
 import pytest
 import torch
@@ -87,7 +88,11 @@ CFGS = [
 ]
 
 
-# normwise gradient error vs the fp32 oracle: 2x the largest value measured on B200 (profiles/r2_test_measurements.json)
+# Normwise gradient error vs the fp32 ORACLE on these micro cases (random weights, random +-1 inputs, random output
+# gradients, 128 / 1000 points): measured 0.06-0.14 on B200 (profiles/r2_test_measurements.json) -- almost all of it ReLU
+# masks of near-zero pre-activations flipping under bf16 rounding, which a handful of points cannot average out (the same
+# kernels give <= 1.2e-2 on a real 8192-ray step, tests/test_fullsize_gpu.py, and <= 1e-2 against the bf16-emulating
+# reference below).  The bound is 1.1x / 1.4x the measured maxima; it is a regression guard, not the parity claim.
 GRAD_VS_FP32 = {1000: 1.5e-1, 128: 1.5e-1}
 
 
@@ -177,3 +182,56 @@ def test_sinusoidal_fused_image_net():
         y_b = net.forward_sinusoidal(X.cuda().float(), enc.freq_bands("cuda"))
     assert rel_max(y_a.cpu(), y_ref) < 1e-2
     assert rel_max(y_b.cpu(), y_ref) < 1e-2
+
+
+def test_two_forwards_before_backward_and_chunked_run_model():
+    """the saved activations live in ONE workspace per model.  A second saving forward before the first
+    one's backward (chunked callers: run_model's netchunk loop, batchify_rays, render_rays_eval with network_fine=None)
+    must not corrupt the first one's gradient: its backward recomputes what was overwritten."""
+    from nerf_meets_mlx_b200.models import NeRF
+    from nerf_meets_mlx_b200.models.NeRF import run_model
+    from nerf_meets_mlx_b200.models import embedding
+    cfg = CFGS[0]
+    torch.manual_seed(0)
+    net = NeRF(device="cuda", n_freqs_pos=10, n_freqs_dir=4, **cfg)
+    cin = cfg["channel_input"] + cfg["channel_input_views"]
+    xa, xb = torch.randn(300, cin, device="cuda").clamp(-1, 1), torch.randn(500, cin, device="cuda").clamp(-1, 1)
+    ga, gb = torch.randn(300, 4, device="cuda"), torch.randn(500, 4, device="cuda")
+
+    def grad_of(x, g):
+        net.flat.grad = None
+        (net.forward(x) * g).sum().backward()
+        return net.flat.grad.clone()
+    ref = grad_of(xa, ga) + grad_of(xb, gb)
+    n0 = net.recomputed_backwards
+    net.flat.grad = None
+    ya, yb = net.forward(xa), net.forward(xb)     # the second forward overwrites the first one's activations
+    ((ya * ga).sum() + (yb * gb).sum()).backward()
+    assert net.recomputed_backwards == n0 + 1
+    assert float((net.flat.grad - ref).norm() / ref.norm()) < 1e-5
+    # chunked run_model (netchunk < points: several model.forward calls inside one autograd graph)
+    e_pos, _ = embedding.get_embedder(10)
+    e_dir, _ = embedding.get_embedder(4)
+    pos = torch.randn(40, 16, 3, device="cuda")
+    dirs = torch.nn.functional.normalize(torch.randn(40, 3, device="cuda"), dim=-1)
+    g = torch.randn(40, 16, 4, device="cuda")
+    net.flat.grad = None
+    (run_model(pos, e_pos, dirs, e_dir, net, netchunk=1 << 20) * g).sum().backward()
+    one = net.flat.grad.clone()
+    net.flat.grad = None
+    n0 = net.recomputed_backwards
+    (run_model(pos, e_pos, dirs, e_dir, net, netchunk=256) * g).sum().backward()   # 3 chunks
+    assert net.recomputed_backwards >= n0 + 2
+    assert float((net.flat.grad - one).norm() / one.norm()) < 1e-5
+    # no-view-dir net (use_viewdirs=False configuration of the reference)
+    net2 = NeRF(device="cuda", **CFGS[2])
+    x1, x2 = torch.randn(200, CFGS[2]["channel_input"], device="cuda"), torch.randn(333, CFGS[2]["channel_input"], device="cuda")
+    net2.flat.grad = None
+    (net2.forward(x1).sum() * 1.0).backward()
+    r1 = net2.flat.grad.clone()
+    net2.flat.grad = None
+    (net2.forward(x2).sum() * 1.0).backward()
+    r2 = net2.flat.grad.clone()
+    net2.flat.grad = None
+    (net2.forward(x1).sum() + net2.forward(x2).sum()).backward()
+    assert float((net2.flat.grad - (r1 + r2)).norm() / (r1 + r2).norm()) < 1e-5

@@ -47,7 +47,7 @@ def test_train_iteration_vs_oracle(measured):
     gc = tr.coarse.split_flat(tr._g_coarse)
     for name, g in ref["grads_coarse"].items():
         e = measured("train_iteration_96rays/coarse_grad_vs_fp32_oracle", float((gc[name].cpu() - g).norm() / (g.norm() + 1e-20)))
-        assert e < 1.5e-1, (name, e)
+        assert e < 5.5e-2, (name, e)  # 2 x the measured 2.7e-2 (profiles/r2_test_measurements.json); full size: 6.4e-3
     # fine depths: sorted, same count, close to the oracle's (weights come from a bf16 coarse net)
     zf = out["z_fine"].cpu().numpy()
     assert zf.shape == ref["z_fine"].shape and np.all(np.diff(zf, axis=-1) >= 0)
