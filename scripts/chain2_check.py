@@ -1,7 +1,8 @@
 """chain2 (CTA pairs, two tiles in ping-pong; NMX_DISABLE_CHAIN2=1 turns it off) vs the one-tile-per-CTA chain: the inference
-forward (chain2 when enabled) against the training forward (always the one-tile chain) on the same inputs, and timing.
+forward (chain2 when enabled) against the training forward (NMX_DISABLE_CHAIN2T=1: the one-tile chain) on the same inputs, and timing.
 
-    python scripts/chain2_check.py      # NMX_CHAIN2_DBG selects the timing-only experiments
+    python scripts/chain2_check.py      # NMX_CHAIN2_DBG selects the timing-only experiments (experiments build only:
+                                        # python -m nerf_meets_mlx_b200.build --experiments; the default build ignores it)
 """
 import sys, time
 import torch

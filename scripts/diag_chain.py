@@ -1,4 +1,5 @@
-"""MMA issue-rate probe + event trace of the fused forward chain (CTA 0)."""
+"""MMA issue-rate probe + event trace of the fused forward chain (CTA 0).
+The event trace (NMX_CHAIN_DBG=4) exists only in an experiments build: python -m nerf_meets_mlx_b200.build --experiments"""
 import ctypes
 import os
 import sys
