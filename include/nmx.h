@@ -99,6 +99,13 @@ int nmx_composite_bwd(const float* raw, const float* z, const float* rays_d, int
                       const float* d_acc, const float* d_depth, const float* d_weights, float* d_raw,
                       int64_t B, int n, void* stream);
 
+/* The loss functions of the training step (mlx_mse_coarse / mlx_mse_fine, __test_nerf.py:83-88, 111-124) fused:
+ * rgb = raw2outputs(raw, z, rays_d)[0]; loss[0] += mean((rgb - target)^2) (caller zeroes loss); d_raw = d loss / d raw.
+ * target [B,3]; optional outputs rgb [B,3], weights [B,n] (NULL to skip).  n <= 256. */
+int nmx_composite_loss_fwd_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, int white_bkgd,
+                               const float* target, float* loss, float* d_raw, float* rgb, float* weights,
+                               int64_t B, int n, void* stream);
+
 /* ---------------------------------------------------------------- inverse-CDF resampling (K5) */
 /* sample_from_inverse_cdf_torch (sampling/__init__.py:101-178) + sort-merge (rendering/render.py:225).
  * z [B,n], weights [B,n], u [B,N].  cdf_in [B,n+1] optional (NULL -> built in-kernel: fp64 sum / prefix).

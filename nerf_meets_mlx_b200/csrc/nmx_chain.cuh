@@ -88,6 +88,23 @@ struct Chain2Launch {
 };
 int launch_chain2(const Chain2Launch& a, cudaStream_t stream);
 
+// Per-launch preparation of the pair chains in one kernel (nmx_chain2.cu `ray_prep_kernel`): the constants block
+// (biases, w_alpha, w_rgb: 3328 floats), the per-ray view-dir term of the dir layer [rays, 128] fp32 and, when dir_pe is
+// non-null, the bf16 per-ray PE(dir) table [rays, 64].
+struct RayPrep {
+  const float* params;
+  int bias_off[10];
+  int alpha_w_off, rgb_w_off;
+  const float* rays; int ray_stride;
+  long long b0, B;             // first ray / number of rays
+  int n_freqs_dir;
+  int dir_w_off, dir_ldw;
+  float* consts;
+  float* dir_bias;
+  void* dir_pe;
+};
+int launch_ray_prep(const RayPrep& rp, cudaStream_t stream);
+
 // Training forward of the same net on CTA pairs (nmx_chain2t.cu): saves h_0 .. h_7, hd, the ReLU sign bits and the
 // encoded input tile X0, in the layouts the one-tile training chain (nmx_chain.cu) writes.
 struct Chain2TrainLaunch {
@@ -101,7 +118,8 @@ struct Chain2TrainLaunch {
   const float* rays; int ray_stride; const float* z;
   int n_per_ray; int in_dir;   // in_dir = encoded view-dir channels (27)
   int dir_w_off, dir_ldw;
-  const void* dir_pe;          // [rays, 64] bf16 per-ray view-dir PE (encode_dirs_kernel)
+  void* dir_pe;                // [rays, 64] bf16 per-ray view-dir PE table (written by the launch's ray_prep_kernel)
+  int n_freqs_dir;
   float* scratch;              // chain2_train_scratch_bytes(rays): constants block + per-ray dir-layer term
   void* save_base; long long save_rows; long long cap;  // activation store [(D + 1) * cap, 256] bf16
   void* hd;                    // [P, 128] bf16

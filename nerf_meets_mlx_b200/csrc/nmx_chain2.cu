@@ -423,55 +423,73 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
   if (warp == kEncWarp0) tmem_dealloc_pair<512>(tmem_base);
 }
 
-// aligned copy of what the epilogue reads per column: bias [kNL][256] (zero padded), w_alpha [256], w_rgb [3][128]
-__global__ void chain2_consts_kernel(const float* __restrict__ params, Chain2Params prm, float* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNL * 256 + 256 + 384; i += gridDim.x * blockDim.x) {
-    float v;
-    if (i < kNL * 256) {
-      const int l = i >> 8, c = i & 255;
-      v = c < (l == kNL - 1 ? 128 : 256) ? params[prm.bias_off[l] + c] : 0.0f;
-    } else if (i < kNL * 256 + 256) {
-      v = params[prm.alpha_w_off + (i - kNL * 256)];
-    } else {
-      v = params[prm.rgb_w_off + (i - kNL * 256 - 256)];
-    }
-    out[i] = v;
-  }
-}
-
-// per-ray view-dir term of the dir layer: out[b, o] = sum_k bf16(W_dir[o, W + k]) * bf16(PE(dir_b)[k])  (fp32 accumulate,
-// increasing k).  A block keeps the 27 x 128 bf16-rounded weight columns in shared memory and walks over rays.
+// Everything the pair chains need per launch besides the weights, in ONE kernel (was three launches):
+//  * consts: aligned copy of what the epilogue reads per column: bias [kNL][256] (zero padded), w_alpha [256],
+//    w_rgb [3][128] (blocks 0..25 write 128 entries each);
+//  * per ray: the view-dir encoding PE(dir) (models/embedding.py:35-71, bands k^2, bf16-rounded like every MLP operand),
+//    optionally stored as a bf16 [rays, 64] table (training: X0[:, 64:128] is filled from it), and the view-dir term of
+//    the dir layer out[b, o] = sum_k bf16(W_dir[o, W + k]) * PE(dir_b)[k] (fp32 accumulate, increasing k).  A block keeps
+//    the 27 x 128 bf16-rounded weight columns in shared memory and walks over rays.
 __global__ void __launch_bounds__(128)
-dir_bias_kernel(const float* __restrict__ rays, int ray_stride, long long b0, long long B, int n_freqs_dir,
-                const float* __restrict__ Wd, int ldw, int w_col0, float* __restrict__ out) {
+ray_prep_kernel(const RayPrep a) {
   __shared__ float w_s[64 * 128];
   __shared__ float pe[2][64];
-  const int in_dir = 3 + 6 * n_freqs_dir;
   const int o = threadIdx.x;
-  for (int k = 0; k < in_dir; ++k) w_s[k * 128 + o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldw + w_col0 + k]));
-  int buf = 0;
-  for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
-    if (o < in_dir) {
-      const float* d = rays + (b0 + b) * ray_stride + (ray_stride - 3);
+  {
+    const int i = blockIdx.x * 128 + o;
+    if (i < kNL * 256 + 256 + 384) {
       float v;
-      if (o < 3) v = d[o];
-      else {
-        const int qq = o - 3, k = qq / 6, rr = qq - 6 * k, fn = rr / 3, dd = rr - 3 * fn;
-        const float a = __fmul_rn(d[dd], (float)(k * k));
-        v = fn ? cosf(a) : sinf(a);
+      if (i < kNL * 256) {
+        const int l = i >> 8, c = i & 255;
+        v = c < (l == kNL - 1 ? 128 : 256) ? a.params[a.bias_off[l] + c] : 0.0f;
+      } else if (i < kNL * 256 + 256) {
+        v = a.params[a.alpha_w_off + (i - kNL * 256)];
+      } else {
+        v = a.params[a.rgb_w_off + (i - kNL * 256 - 256)];
       }
-      pe[buf][o] = __bfloat162float(__float2bfloat16_rn(v));
+      a.consts[i] = v;
+    }
+  }
+  const int in_dir = 3 + 6 * a.n_freqs_dir;
+  const float* Wd = a.params + a.dir_w_off;
+  for (int k = 0; k < in_dir; ++k) w_s[k * 128 + o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * a.dir_ldw + 256 + k]));
+  __nv_bfloat16* table = reinterpret_cast<__nv_bfloat16*>(a.dir_pe);
+  int buf = 0;
+  for (long long b = blockIdx.x; b < a.B; b += gridDim.x, buf ^= 1) {
+    if (o < 64) {
+      float v = 0.0f;
+      if (o < in_dir) {
+        const float* d = a.rays + (a.b0 + b) * a.ray_stride + (a.ray_stride - 3);
+        if (o < 3) v = d[o];
+        else {
+          const int qq = o - 3, k = qq / 6, rr = qq - 6 * k, fn = rr / 3, dd = rr - 3 * fn;
+          const float ang = __fmul_rn(d[dd], (float)(k * k));
+          v = fn ? cosf(ang) : sinf(ang);
+        }
+      }
+      const __nv_bfloat16 vb = __float2bfloat16_rn(v);
+      pe[buf][o] = __bfloat162float(vb);
+      if (table != nullptr) table[b * 64 + o] = vb;
     }
     __syncthreads();  // (double-buffered pe: one barrier per ray)
     float acc = 0.0f;
     for (int k = 0; k < in_dir; ++k) acc += w_s[k * 128 + o] * pe[buf][k];
-    out[b * 128 + o] = acc;
+    a.dir_bias[b * 128 + o] = acc;
   }
 }
 
 }  // namespace
 
 namespace nmx {
+
+int launch_ray_prep(const RayPrep& rp, cudaStream_t stream) {
+  if (rp.B <= 0) return 0;
+  long long blocks = rp.B < (long long)kNumSMs * 8 ? rp.B : (long long)kNumSMs * 8;
+  if (blocks < 26) blocks = 26;  // the constants block is written 128 entries per block
+  ray_prep_kernel<<<(unsigned)blocks, 128, 0, stream>>>(rp);
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
 
 int launch_chain2(const Chain2Launch& a, cudaStream_t stream) {
   if (a.P <= 0) return 0;
@@ -493,13 +511,18 @@ int launch_chain2(const Chain2Launch& a, cudaStream_t stream) {
   float* consts = a.dir_bias;
   float* dir_bias = a.dir_bias + 3328;
   prm.consts = consts; prm.dir_bias = dir_bias;
-  chain2_consts_kernel<<<13, 256, 0, stream>>>(a.params, prm, consts);
-  NMX_LAUNCH_CHECK();
   const long long b1 = (a.p0 + a.P - 1) / a.n_per_ray;
   const long long n_rays = b1 - prm.b0 + 1;
-  dir_bias_kernel<<<(unsigned)(n_rays < kNumSMs * 8 ? n_rays : kNumSMs * 8), 128, 0, stream>>>(
-      a.rays, a.ray_stride, prm.b0, n_rays, a.n_freqs_dir, a.params + a.dir_w_off, a.dir_ldw, 256, dir_bias);
-  NMX_LAUNCH_CHECK();
+  {
+    RayPrep rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.params = a.params;
+    for (int l = 0; l < kNL; ++l) rp.bias_off[l] = a.bias_off[l];
+    rp.alpha_w_off = a.alpha_w_off; rp.rgb_w_off = a.rgb_w_off;
+    rp.rays = a.rays; rp.ray_stride = a.ray_stride; rp.b0 = prm.b0; rp.B = n_rays; rp.n_freqs_dir = a.n_freqs_dir;
+    rp.dir_w_off = a.dir_w_off; rp.dir_ldw = a.dir_ldw; rp.consts = consts; rp.dir_bias = dir_bias; rp.dir_pe = nullptr;
+    if ((rc = launch_ray_prep(rp, stream))) return rc;
+  }
   static bool attr[64] = {};
   if (once_per_device(attr)) {
     NMX_CUDA(cudaFuncSetAttribute(mlp_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::kAlloc));

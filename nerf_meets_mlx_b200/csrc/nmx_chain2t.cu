@@ -511,41 +511,6 @@ mlp_chain2_train_kernel(const __grid_constant__ Maps maps, const Params prm) {
   if (warp == kEncWarp0) tmem_dealloc_pair<512>(tmem_base);
 }
 
-// aligned copy of what the epilogue reads per column: bias [kNL][256] (zero padded), w_alpha [256], w_rgb [3][128]
-__global__ void chain2t_consts_kernel(const float* __restrict__ params, const Chain2TrainLaunch a, float* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kNL * 256 + 256 + 384; i += gridDim.x * blockDim.x) {
-    float v;
-    if (i < kNL * 256) {
-      const int l = i >> 8, c = i & 255;
-      v = c < (l == kNL - 1 ? 128 : 256) ? params[a.bias_off[l] + c] : 0.0f;
-    } else if (i < kNL * 256 + 256) {
-      v = params[a.alpha_w_off + (i - kNL * 256)];
-    } else {
-      v = params[a.rgb_w_off + (i - kNL * 256 - 256)];
-    }
-    out[i] = v;
-  }
-}
-
-// per-ray view-dir term of the dir layer (same arithmetic as nmx_chain2.cu's dir_bias_kernel, reading the bf16 PE(dir)
-// table the training path builds anyway): out[b, o] = sum_k bf16(W_dir[o, W + k]) * PE(dir_b)[k], increasing k
-__global__ void __launch_bounds__(128)
-dir_bias_from_table_kernel(const __nv_bfloat16* __restrict__ dir_pe, long long B, int in_dir, const float* __restrict__ Wd,
-                           int ldw, int w_col0, float* __restrict__ out) {
-  __shared__ float w_s[64 * 128];
-  __shared__ float pe[2][64];
-  const int o = threadIdx.x;
-  for (int k = 0; k < in_dir; ++k) w_s[k * 128 + o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * ldw + w_col0 + k]));
-  int buf = 0;
-  for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
-    if (o < in_dir) pe[buf][o] = __bfloat162float(dir_pe[b * 64 + o]);
-    __syncthreads();
-    float acc = 0.0f;
-    for (int k = 0; k < in_dir; ++k) acc += w_s[k * 128 + o] * pe[buf][k];
-    out[b * 128 + o] = acc;
-  }
-}
-
 // ================================================================================================ backward
 // Data-gradient chain of the same net on CTA pairs, two tiles in ping-pong (the pair version of nmx_chain.cu MODE 1):
 //   step A : d_hd = (d_rgb W_rgb) * [hd > 0] on the CUDA cores -> chunks 0,1 (A operand of layer 0) and the d_hd store
@@ -1008,12 +973,17 @@ int launch_chain2_train(const Chain2TrainLaunch& a, cudaStream_t stream) {
   float* consts = a.scratch;          // [constants block (13 KB) | per-ray dir bias]
   float* dir_bias = a.scratch + 3328;
   prm.consts = consts; prm.dir_bias = dir_bias;
-  chain2t_consts_kernel<<<13, 256, 0, stream>>>(a.params, a, consts);
-  NMX_LAUNCH_CHECK();
   const long long n_rays = (a.P + a.n_per_ray - 1) / a.n_per_ray;
-  dir_bias_from_table_kernel<<<(unsigned)(n_rays < kNumSMs * 8 ? n_rays : kNumSMs * 8), 128, 0, stream>>>(
-      (const __nv_bfloat16*)a.dir_pe, n_rays, a.in_dir, a.params + a.dir_w_off, a.dir_ldw, 256, dir_bias);
-  NMX_LAUNCH_CHECK();
+  {
+    RayPrep rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.params = a.params;
+    for (int l = 0; l < kNL; ++l) rp.bias_off[l] = a.bias_off[l];
+    rp.alpha_w_off = a.alpha_w_off; rp.rgb_w_off = a.rgb_w_off;
+    rp.rays = a.rays; rp.ray_stride = a.ray_stride; rp.b0 = 0; rp.B = n_rays; rp.n_freqs_dir = a.n_freqs_dir;
+    rp.dir_w_off = a.dir_w_off; rp.dir_ldw = a.dir_ldw; rp.consts = consts; rp.dir_bias = dir_bias; rp.dir_pe = a.dir_pe;
+    if ((rc = launch_ray_prep(rp, stream))) return rc;
+  }
   fill_x0_dir_kernel<<<grid_for(a.P * 8, 256, 16), 256, 0, stream>>>((const uint4*)a.dir_pe, (uint4*)a.x0, a.P, a.n_per_ray);
   NMX_LAUNCH_CHECK();
   static bool attr[64] = {};

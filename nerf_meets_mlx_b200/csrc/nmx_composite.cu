@@ -191,6 +191,102 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
+// Training step in one pass over a ray (the loss functions of the reference, __test_nerf.py:83-88 and :111-124):
+//   rgb = raw2outputs(raw, z, d)[0] ; loss += mean((rgb - target)^2) ; d_raw = d loss / d raw.
+// Same forward and backward arithmetic as the two kernels above; the per-ray colour never goes to HBM and the loss
+// gradient 2 (rgb - target) / (3 B) is formed in registers.  Optional outputs: rgb [B,3], weights [B,n].
+template <int NCHUNK>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_loss_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                      int d_stride, int white_bkgd, const float* __restrict__ target, float inv_count,
+                      float* __restrict__ loss, float* __restrict__ d_raw, float* __restrict__ rgb_out,
+                      float* __restrict__ weights, int64_t B, int n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+  float loss_acc = 0.0f;  // this warp's share of sum (rgb - target)^2 (lane 0)
+  for (int64_t b = warp0; b < B; b += nwarps) {
+    const float* zr = z + b * n;
+    const float4* rawr = reinterpret_cast<const float4*>(raw) + b * n;
+    float norm = ray_norm(rays_d + b * d_stride);
+    float w_[NCHUNK], T_[NCHUNK], tau_[NCHUNK], delta_[NCHUNK];
+    float4 rv_[NCHUNK];
+    float carry = 0.0f, aa = 0.0f, ar = 0.0f, ag = 0.0f, ab = 0.0f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      bool valid;
+      float zi;
+      load_chunk(zr, rawr, nullptr, 0.0f, n, c, lane, norm, zi, delta_[c], rv_[c], valid);
+      int i = c * 32 + lane;
+      float tau = __fmul_rn(delta_[c], rv_[c].w);
+      float tau_scan = (valid && i < n - 1) ? tau : 0.0f;
+      float incl = warp_scan_incl(tau_scan, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.0f;
+      float S = carry + excl;
+      float T = expf(-S);
+      float alpha = 1.0f - expf(-fmaxf(tau, 0.0f));
+      float w = valid ? alpha * T : 0.0f;
+      if (weights != nullptr && valid) weights[b * n + i] = w;
+      tau_[c] = tau;
+      T_[c] = valid ? T : 0.0f;
+      w_[c] = w;
+      ar += w * rv_[c].x;
+      ag += w * rv_[c].y;
+      ab += w * rv_[c].z;
+      aa += w;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    ar = warp_sum(ar);
+    ag = warp_sum(ag);
+    ab = warp_sum(ab);
+    aa = warp_sum(aa);
+    if (white_bkgd) {
+      const float bg = 1.0f - aa;
+      ar += bg; ag += bg; ab += bg;
+    }
+    const float dr = ar - target[b * 3 + 0], dg = ag - target[b * 3 + 1], db = ab - target[b * 3 + 2];
+    if (lane == 0) {
+      loss_acc += dr * dr + dg * dg + db * db;
+      if (rgb_out != nullptr) { rgb_out[b * 3 + 0] = ar; rgb_out[b * 3 + 1] = ag; rgb_out[b * 3 + 2] = ab; }
+    }
+    const float gr = 2.0f * dr * inv_count, gg = 2.0f * dg * inv_count, gb = 2.0f * db * inv_count;
+    const float g_acc = white_bkgd ? -(gr + gg + gb) : 0.0f;
+    float rcarry = 0.0f;
+#pragma unroll
+    for (int c = NCHUNK - 1; c >= 0; --c) {
+      int i = c * 32 + lane;
+      bool valid = i < n;
+      float g = gr * rv_[c].x + gg * rv_[c].y + gb * rv_[c].z + g_acc;
+      float gw = valid ? g * w_[c] : 0.0f;
+      float rincl = warp_rscan_incl(gw, lane);
+      float rexcl = __shfl_down_sync(0xffffffffu, rincl, 1);
+      if (lane == 31) rexcl = 0.0f;
+      float suffix_excl = rcarry + rexcl;
+      float tau = tau_[c];
+      float dalpha = (tau > 0.0f) ? expf(-tau) : 0.0f;
+      float dtau = g * T_[c] * dalpha;
+      if (i < n - 1) dtau -= suffix_excl;
+      float dsigma = delta_[c] * dtau;
+      if (valid) {
+        float wv = w_[c];
+        reinterpret_cast<float4*>(d_raw)[b * n + i] = make_float4(wv * gr, wv * gg, wv * gb, dsigma);
+      }
+      rcarry += __shfl_sync(0xffffffffu, rincl, 0);
+    }
+  }
+  // one atomic per block
+  __shared__ float s_loss[kWarpsPerBlock];
+  if (lane == 0) s_loss[threadIdx.x >> 5] = loss_acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) t += s_loss[w];
+    atomicAdd(loss, t * inv_count);
+  }
+}
+
 }  // namespace
 
 extern "C" int nmx_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
@@ -229,6 +325,32 @@ extern "C" int nmx_composite_bwd(const float* raw, const float* z, const float* 
   else if (nch <= 6) NMX_BWD(6);
   else NMX_BWD(8);
 #undef NMX_BWD
+  NMX_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused training pass of one net: raw2outputs forward, MSE against `target` [B,3] (loss [1] is ACCUMULATED: the caller
+// zeroes it; mean over 3 B elements) and the gradient w.r.t. raw [B,n,4], one kernel.  rgb [B,3] and weights [B,n] are
+// optional outputs (NULL to skip).  n <= 256.
+extern "C" int nmx_composite_loss_fwd_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                          int white_bkgd, const float* target, float* loss, float* d_raw, float* rgb,
+                                          float* weights, int64_t B, int n, void* stream) {
+  NMX_CHECK_ARG(B >= 0 && n >= 1 && d_stride >= 3 && n <= 256, "B >= 0, 1 <= n <= 256, d_stride >= 3");
+  if (B == 0) return 0;
+  NMX_CHECK_ARG(raw && z && rays_d && target && loss && d_raw, "raw, z, rays_d, target, loss, d_raw must be non-null");
+  int blocks = grid_for(B, kWarpsPerBlock, 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float inv_count = 1.0f / (float)(3 * B);
+  int nch = (n + 31) / 32;
+#define NMX_CL(NC)                                                                                                  \
+  composite_loss_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, s>>>(raw, z, rays_d, d_stride, white_bkgd, target, \
+                                                                    inv_count, loss, d_raw, rgb, weights, B, n)
+  if (nch <= 1) NMX_CL(1);
+  else if (nch <= 2) NMX_CL(2);
+  else if (nch <= 4) NMX_CL(4);
+  else if (nch <= 6) NMX_CL(6);
+  else NMX_CL(8);
+#undef NMX_CL
   NMX_LAUNCH_CHECK();
   return 0;
 }

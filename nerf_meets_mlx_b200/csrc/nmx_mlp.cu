@@ -963,6 +963,7 @@ int forward_chain2_train(const Ctx& c, int64_t P, float* out, const EncIn& enc) 
   a.alpha_w_off = (int)p->alpha.w_off; a.alpha_b_off = (int)p->alpha.b_off;
   a.rgb_w_off = (int)p->rgb.w_off; a.rgb_b_off = (int)p->rgb.b_off;
   a.rays = enc.rays; a.ray_stride = enc.ray_stride; a.z = enc.z; a.n_per_ray = enc.n; a.in_dir = p->in_dir;
+  a.n_freqs_dir = p->cfg.n_freqs_dir;
   a.dir_w_off = (int)p->dir.w_off; a.dir_ldw = p->dir.in;
   // per-ray scratch inside the dirpe_bytes region: [PE(dir) table: rays x 128 B | constants + dir-layer term: 512 B / ray]
   const int64_t n_rays = (P + enc.n - 1) / enc.n;
@@ -1000,11 +1001,13 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   c.enc_kind = enc_kind;
   if (c.training) {
     c.al = act_layout(p, p->max_points, true);
-    if ((rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
+    const bool pair_train = chain_eligible(p) && chain2t_ok(p, enc_kind, n, P);
+    // (the pair kernel's own preparation launch builds the per-ray view-dir table: no encode_chunk)
+    if (!pair_train && (rc = encode_chunk(c, x_or_rays, ray_stride, z, bands, 0, P, n))) return rc;
     if (chain_eligible(p)) {
       EncIn ei{x_or_rays, ray_stride, z, 0, n};
-      p->bits_word_major = chain2t_ok(p, enc_kind, n, P) ? 1 : 0;
-      if (p->bits_word_major) return forward_chain2_train(c, P, out, ei);
+      p->bits_word_major = pair_train ? 1 : 0;
+      if (pair_train) return forward_chain2_train(c, P, out, ei);
       return forward_chain(c, P, p->max_points, out, out_cols, &ei);
     }
     return forward_chunk(c, P, out, out_cols);

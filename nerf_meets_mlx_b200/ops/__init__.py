@@ -200,6 +200,23 @@ def composite_bwd(raw, z, rays_d, d_rgb, d_disp=None, d_acc=None, d_depth=None, 
     return d_raw
 
 
+def composite_loss_fwd_bwd(raw, z, rays_d, target, white_bkgd=False, want_weights=False, want_rgb=False):
+    """Fused training pass: raw2outputs -> mean((rgb - target)^2) -> gradient w.r.t. raw, one kernel.
+    Returns (loss [1], d_raw [B,n,4], weights [B,n,1] or None, rgb [B,3] or None)."""
+    raw, z, target = _f32c(raw), _f32c(z), _f32c(target)
+    rays_d, d_stride = _rows3(rays_d)
+    require_cuda(raw, z, target)
+    B, n = z.shape
+    dev = z.device
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    d_raw = torch.empty((B, n, 4), dtype=torch.float32, device=dev)
+    weights = torch.empty((B, n, 1), dtype=torch.float32, device=dev) if want_weights else None
+    rgb = torch.empty((B, 3), dtype=torch.float32, device=dev) if want_rgb else None
+    call("nmx_composite_loss_fwd_bwd", ptr(raw), ptr(z), ptr(rays_d), i32(d_stride), i32(1 if white_bkgd else 0), ptr(target),
+         ptr(loss), ptr(d_raw), ptr(rgb), ptr(weights), i64(B), i32(n), stream())
+    return loss, d_raw, weights, rgb
+
+
 # ----------------------------------------------------------------------------------------- resampling
 def sample_pdf(z, weights, u, eps=1e-5, cdf=None, want_inds=False, want_cdf=False, want_merged=True, want_imp=True):
     z, u = _f32c(z), _f32c(u)

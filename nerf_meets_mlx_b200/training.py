@@ -117,9 +117,10 @@ class NeRFTrainer:
         B, n = z.shape
         rays_d = rays[:, 3:6]  # strided view: the compositing kernels take the row stride
         raw = model._fwd_raw(1, rays, z, None, B, n, save=True)
-        rgb, _, _, weights, _ = ops.composite_fwd(raw.view(B, n, 4), z, rays_d, white_bkgd=white_bkgd)
-        loss, d_rgb = ops.mse_fwd_bwd(rgb, target)
-        d_raw = ops.composite_bwd(raw.view(B, n, 4), z, rays_d, d_rgb, white_bkgd=white_bkgd)
+        # compositing forward + MSE + compositing backward in one kernel; the weights are only needed when the fine
+        # pass resamples from THIS forward (reuse_coarse_forward, a declared deviation)
+        loss, d_raw, weights, _ = ops.composite_loss_fwd_bwd(raw.view(B, n, 4), z, rays_d, target, white_bkgd=white_bkgd,
+                                                             want_weights=self.reuse_coarse_forward)
         model._bwd_raw(d_raw.view(B * n, 4), B * n, out=g_buf)
         return loss, weights
 

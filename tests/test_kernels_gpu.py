@@ -370,3 +370,24 @@ def test_custom_ops_opcheck(ops):
     (rgb.sum() + 0.5 * acc.sum()).backward()
     want = ops.composite_bwd(raw.detach(), z, d, torch.ones(B, 3, device="cuda"), d_acc=torch.full((B, 1), 0.5, device="cuda"))
     np.testing.assert_array_equal(raw.grad.cpu().numpy(), want.cpu().numpy())
+
+
+def test_composite_loss_fused_equals_separate_kernels(ops):
+    """nmx_composite_loss_fwd_bwd (compositing + MSE + its gradient in one kernel) == composite_fwd -> mse_fwd_bwd ->
+    composite_bwd: rgb and weights bit-identical, d_raw and loss to fp32 contraction / summation order."""
+    rng = np.random.default_rng(11)
+    for B, n, wb in ((37, 64, True), (50, 192, False), (5, 7, True), (1024, 64, True)):
+        raw = rng.standard_normal(size=(B, n, 4)).astype(np.float32)
+        raw[..., 3] *= 2.0
+        z = np.sort(rng.uniform(2, 6, size=(B, n)).astype(np.float32), -1)
+        d = rng.standard_normal(size=(B, 3)).astype(np.float32)
+        tgt = rng.random(size=(B, 3)).astype(np.float32)
+        R, Z, D, T = dev(raw), dev(z), dev(d), dev(tgt)
+        rgb, _, _, w, _ = ops.composite_fwd(R, Z, D, white_bkgd=wb)
+        loss, d_rgb = ops.mse_fwd_bwd(rgb, T)
+        d_raw = ops.composite_bwd(R, Z, D, d_rgb, white_bkgd=wb)
+        loss2, d_raw2, w2, rgb2 = ops.composite_loss_fwd_bwd(R, Z, D, T, white_bkgd=wb, want_weights=True, want_rgb=True)
+        assert torch.equal(rgb2, rgb) and torch.equal(w2, w)
+        err = float((d_raw2 - d_raw).abs().max() / d_raw.abs().max())
+        assert err < 1e-6, err
+        assert abs(float(loss2) - float(loss)) <= 1e-5 * abs(float(loss))
