@@ -125,3 +125,40 @@ def test_cta_pair_two_tile_chain_matches_one_tile_chain():
     errs = [float(x) for x in re.findall(r"rel max err ([0-9.e+-]+)", r.stdout)]
     assert len(errs) == 6 and all(e < 2e-3 for e in errs), r.stdout
     assert r.stdout.count("finite=True") == 6
+
+
+@pytest.mark.parametrize("B,n", [(525, 8), (545, 8), (33, 128), (1000, 8), (64, 64), (700, 24)])
+def test_pair_training_chains_match_one_tile_chains(B, n):
+    """The CTA-pair training forward / backward (nmx_chain2t.cu, taken for rays-path passes of >= 4096 points with >= 8
+    samples per ray) against the one-tile training forward (nmx_chain.cu) on the SAME points: the one-tile forward is
+    selected in-process by presenting every ray several times with < 8 of its samples each (below the pair forward's
+    limit); the pair backward then runs on the one-tile forward's row-major sign bits, so both sign-bit layouts are
+    exercised and must give the same gradient.
+    Sizes cover an odd number of 256-point pair tiles (one cluster runs a single tile from the start), a ragged last
+    tile and whole multiples."""
+    from nerf_meets_mlx_b200.models import NeRF
+    torch.manual_seed(B * 1000 + n)
+    net = NeRF(device="cuda", n_freqs_pos=10, n_freqs_dir=4, seed=11, **KW)
+    with torch.no_grad():
+        net.alpha_linear.bias.fill_(0.3)
+        net.mark_params_updated()
+    o = torch.randn(B, 3, device="cuda") * 0.3 + torch.tensor([0.0, 0.0, 4.0], device="cuda")
+    d = torch.nn.functional.normalize(torch.randn(B, 3, device="cuda") - torch.tensor([0.0, 0.0, 2.0], device="cuda"), dim=-1)
+    rays = torch.cat([o, d, torch.full((B, 1), 2.0, device="cuda"), torch.full((B, 1), 6.0, device="cuda"), d], -1).contiguous()
+    z = torch.sort(torch.rand(B, n, device="cuda") * 4 + 2, -1).values.contiguous()
+    P = B * n
+    d_out = torch.randn(P, 4, device="cuda") * 1e-3
+    net.reserve(P, training=True)
+    # pair kernels
+    raw_p = net._fwd_raw(1, rays, z, None, B, n, save=True).clone()
+    g_p = net._bwd_raw(d_out, P).clone()
+    # one-tile forward: rep * B "rays" of k < 8 samples each (same points in the same order)
+    k = max(dv for dv in range(1, 8) if n % dv == 0)
+    rep = n // k
+    rays1 = rays.repeat_interleave(rep, dim=0).contiguous()
+    z1 = z.reshape(B * rep, k).contiguous()
+    raw_1 = net._fwd_raw(1, rays1, z1, None, B * rep, k, save=True).clone()
+    g_1 = net._bwd_raw(d_out, P).clone()
+    assert torch.isfinite(raw_p).all() and torch.isfinite(g_p).all()
+    assert float((raw_p - raw_1).norm() / raw_1.norm()) < 1e-4
+    assert float((g_p - g_1).norm() / g_1.norm()) < 1e-4
