@@ -356,10 +356,12 @@ mlp_chain2_train_kernel(const __grid_constant__ Maps maps, const Params prm) {
         for (int c = 0; c < nck; ++c) {
           const uint32_t par = (c < 2 ? ph01 : ph23) & 1u;
           while (!poll(&st_ready[t * 4 + c], par)) {
+            bool worked = false;
             if (enc_rr < 4 && l > kSkipL) {
               if (!chunk_free) chunk_free = poll(&pos_empty[t], tcnt & 1u);
-              if (chunk_free) encode_group(nrow0, enc_rr++);
+              if (chunk_free) { encode_group(nrow0, enc_rr++); worked = true; }
             }
+            if (!worked) __nanosleep(64);  // nothing to do: do not burn issue slots (and power: the step runs at the cap)
           }
           if (live && lane == 0 && !NMX_DBG(prm, 1)) {
             const uint8_t* src = smem + SmemT::kActOff + (t * 5 + c) * kChunk;
@@ -742,6 +744,7 @@ mlp_chain2_bwd_kernel(const __grid_constant__ MapsB maps, const ParamsB prm) {
       int g = 0;    // next store group of this tile
       int c = 0;    // next chunk of store group g
       while (m < 9 || g < 9) {
+        bool progressed = false;
         if (m < 9) {
           const uint32_t buf = m_total & 1u;
           // the buffer's previous user (two masked steps ago) must have been read by all sixteen epilogue warps
@@ -759,11 +762,13 @@ mlp_chain2_bwd_kernel(const __grid_constant__ MapsB maps, const ParamsB prm) {
             __syncwarp();
             ++m;
             ++m_total;
+            progressed = true;
           }
         }
         if (g < 9) {
           const int nck = g == 0 ? 2 : 4;
           if (bar_poll(&st_ready[t * 4 + c], (c < 2 ? ph01 : ph23) & 1u, lane)) {
+            progressed = true;
             if (live && lane == 0) {
               const uint8_t* src = smem + SmemB::kActOff + (t * 4 + c) * kChunk;
               if (g == 0) tma_store_2d(&maps.hd, src, c * 64, row0);
@@ -784,6 +789,7 @@ mlp_chain2_bwd_kernel(const __grid_constant__ MapsB maps, const ParamsB prm) {
             }
           }
         }
+        if (!progressed) __nanosleep(64);
       }
     }
     if (lane == 0) tma_store_wait<0>();
