@@ -46,9 +46,11 @@ int launch_colsum(const void* Y, int ld, int col0, int N, int64_t P, float* out,
 namespace nmx {
 
 // ---- batched weight gradients: every wgrad of one backward pass in ONE launch (nmx_wgrad_batch.cu).
-// All operands live in at most four row-major bf16 tensors (the saved-activation region, the saved-dY region, the
-// encoded-input tile X0 and d_hd), addressed per job by (tensor, first row, first column).
+// Operands are row-major bf16 tensors addressed per job by (tensor, first row, first column): either a few whole
+// regions (saved activations, saved dY, X0, d_hd: the fused chains write whole 128-row tiles, so rows past P are finite)
+// or one tensor per slot with rows = P (layer-by-layer path: its stores are clipped at P, and TMA zero-fills the rest).
 constexpr int kMaxWgradJobs = 12;
+constexpr int kMaxWgradTensors = 26;
 struct WgradBatchTensor { const void* base; int64_t rows; int cols; };  // row-major bf16 [rows, cols], ld = cols
 struct WgradBatchJob {
   int dy_t, x_t, x2_t;           // tensor indices (x2_t < 0: no second operand)
@@ -60,7 +62,7 @@ struct WgradBatchJob {
   float* dW2; int ldw2, w2_col, n_valid2;  // second operand: 64 columns of tensor x2_t
 };
 struct WgradBatchDesc {
-  int n_tensors; WgradBatchTensor t[4];
+  int n_tensors; WgradBatchTensor t[kMaxWgradTensors];
   int n_jobs; WgradBatchJob job[kMaxWgradJobs];
   int64_t P;                     // points (contraction length), the same for every job
 };

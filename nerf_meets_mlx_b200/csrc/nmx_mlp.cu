@@ -80,7 +80,9 @@ ActLayout act_layout(const nmx_mlp_plan* p, int64_t cap, bool training) {
   a.g_stride = hbytes;
   if (training) {
     // fused backward chain: every layer's dY is kept for the wgrad kernels (slots 0..D-1 = dY_l, slot D = d_feature)
-    a.g0 = off; off += hbytes * (chain_bwd_eligible(p) ? p->D + 1 : 2);
+    // every layer's dY in its own slot where ALL weight gradients run as one batched launch: the fused backward chain,
+    // and the layer-by-layer path of nets without a view-dir head
+    a.g0 = off; off += hbytes * ((chain_bwd_eligible(p) || !p->cfg.use_viewdirs) ? p->D + 1 : 2);
     a.ghd = off; off += align256(cap * (p->W / 2) * 2);
     // ReLU sign bits (32 B per point and slot): slots 0..D-1 = h_l, slot D = hd
     a.bits = off; if (chain_bwd_eligible(p)) off += align256(cap * 32) * (p->D + 1);
@@ -1300,6 +1302,61 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
     }
     return 0;
   }
+  static int64_t l2_rows = -1;
+  if (l2_rows < 0) { const char* e = getenv("NMX_BWD_L2_ROWS"); l2_rows = e ? atoll(e) : 0; }
+  static int64_t noview_batch_max = -1;  // same cross-over as the chain path's batched launch
+  if (noview_batch_max < 0) {
+    const char* e = getenv("NMX_WGRAD_BATCH_MAX_POINTS");
+    noview_batch_max = getenv("NMX_DISABLE_WGRAD_BATCH") ? 0 : (e ? atoll(e) : 200000);
+  }
+  if (!p->cfg.use_viewdirs && P <= noview_batch_max && l2_rows == 0 && p->D <= kMaxWgradJobs) {
+    // Nets without a view-dir head (image learning, the hash grid's tiny MLP), layer by layer: the data-gradient GEMMs
+    // keep every dY in its own slot and ALL weight gradients run as one batched launch afterwards (was one 8-10 us
+    // launch per layer: the C1 step is launch-bound).
+    if ((rc = launch_head_bwd(W, p->cfg.out_ch, hl, W, params + p->outl.w_off, d_out, out_cols, 0, P, d_params + p->outl.w_off,
+                              d_params + p->outl.b_off, c.G(p->D - 1), W, s))) return rc;
+    for (int l = p->D - 1; l >= 1; --l) {  // dY_{l-1} = (dY_l W_l[:, h part]) * [h_{l-1} > 0]
+      GemmDesc g{};
+      g.A0 = c.G(l); g.a0_rows = P; g.a0_cols = W; g.a0_ld = W; g.a0_k = W;
+      g.B = c.ws + p->wt_off[l]; g.b_rows = W; g.b_cols = W; g.b_ld = W;
+      g.M = P; g.N = W; g.D = c.G(l - 1); g.ldd = W; g.mask = c.H(l - 1); g.ldmask = W;
+      if ((rc = launch_gemm(g, s))) return rc;
+    }
+    if (d_input != nullptr) {
+      bool acc = false;
+      if (skip_l > 0 && skip_l < p->D) {
+        if ((rc = input_grad(c.G(skip_l), 0, P, W, false))) return rc;
+        acc = true;
+      }
+      if ((rc = input_grad(c.G(0), 0, P, 0, acc))) return rc;
+    }
+    WgradBatchDesc bd;
+    memset(&bd, 0, sizeof(bd));
+    bd.P = P;
+    int nt = 0;
+    bd.t[nt++] = {c.X0(), P, p->x0_cols};  // tensor 0: encoded inputs; then one tensor per dY / activation slot (rows = P)
+    for (int l = p->D - 1; l >= 0; --l) {
+      const LinearRef& r = p->trunk[l];
+      WgradBatchJob& g = bd.job[bd.n_jobs++];
+      bd.t[nt] = {c.G(l), P, W};
+      g.dy_t = nt++; g.dy_row0 = 0; g.dy_col = 0; g.M = W; g.x2_t = -1;
+      g.dW = d_params + r.w_off; g.ldw = r.in; g.db = d_params + r.b_off;
+      if (l == 0) {
+        g.x_t = 0; g.x_row0 = 0; g.x_col = 0; g.N = p->pos_pad; g.w_col = 0; g.n_valid = p->in_pos;
+      } else {
+        bd.t[nt] = {c.H(l - 1), P, W};
+        g.x_t = nt++; g.x_row0 = 0; g.x_col = 0; g.N = W; g.n_valid = W;
+        if (r.in == W + p->in_pos) {  // skip layer: [x_pos | h] against one read of dY
+          g.w_col = p->in_pos;
+          g.x2_t = 0; g.x2_row0 = 0; g.x2_col = 0; g.dW2 = g.dW; g.ldw2 = r.in; g.w2_col = 0; g.n_valid2 = p->in_pos;
+        } else {
+          g.w_col = 0;
+        }
+      }
+    }
+    bd.n_tensors = nt;
+    return launch_wgrad_batch(bd, s);
+  }
   // Layer-by-layer path (nets the fused chain does not cover).  With NMX_BWD_L2_ROWS=R the pass runs over windows of
   // R points so that the two ping-pong gradient buffers (always the SAME first R rows) stay L2-resident.
   auto run_window = [&](int64_t r0, int64_t rows) -> int {
@@ -1374,8 +1431,6 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
     }
     return 0;
   };
-  static int64_t l2_rows = -1;
-  if (l2_rows < 0) { const char* e = getenv("NMX_BWD_L2_ROWS"); l2_rows = e ? atoll(e) : 0; }
   if (l2_rows > 0 && l2_rows % 128 == 0) {
     for (int64_t r0 = 0; r0 < P; r0 += l2_rows)
       if ((rc = run_window(r0, P - r0 < l2_rows ? P - r0 : l2_rows))) return rc;

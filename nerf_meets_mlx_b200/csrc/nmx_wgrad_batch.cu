@@ -54,7 +54,7 @@ struct BatchArgs {
   int n_jobs, total_kb;
   JobArgs job[kMaxWgradJobs];
 };
-struct BatchMaps { CUtensorMap t[4]; };
+struct BatchMaps { CUtensorMap t[kMaxWgradTensors]; };
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_batch_kernel(const __grid_constant__ BatchMaps maps, const __grid_constant__ BatchArgs args) {
@@ -215,11 +215,12 @@ namespace nmx {
 
 int launch_wgrad_batch(const WgradBatchDesc& d, cudaStream_t stream) {
   if (d.P <= 0 || d.n_jobs <= 0) return 0;
-  if (d.n_jobs > kMaxWgradJobs || d.n_tensors < 1 || d.n_tensors > 4) { set_error("wgrad_batch: 1..%d jobs, 1..4 tensors", kMaxWgradJobs); return NMX_E_BADARG; }
+  if (d.n_jobs > kMaxWgradJobs || d.n_tensors < 1 || d.n_tensors > kMaxWgradTensors) { set_error("wgrad_batch: 1..%d jobs, 1..%d tensors", kMaxWgradJobs, kMaxWgradTensors); return NMX_E_BADARG; }
   BatchMaps maps;
   int rc;
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < kMaxWgradTensors; ++t) {
     const WgradBatchTensor& T = d.t[t < d.n_tensors ? t : 0];
+    if (t >= d.n_tensors) { maps.t[t] = maps.t[0]; continue; }
     if (T.rows > 0x7fffffff) { set_error("wgrad_batch: tensor rows exceed the TMA coordinate range"); return NMX_E_BADARG; }
     if ((rc = make_tmap_bf16_2d(&maps.t[t], T.base, (uint64_t)T.rows, (uint64_t)T.cols, (uint64_t)T.cols, 64))) return rc;
   }
