@@ -196,11 +196,15 @@ int nmx_mlp_fwd(nmx_mlp_plan* plan, void* workspace, const float* params, int en
 int nmx_mlp_bwd(nmx_mlp_plan* plan, void* workspace, const float* params, const float* d_out, float* d_params,
                 int64_t P, void* stream);
 /* same, and additionally the gradient w.r.t. the (already encoded, enc_kind 0) POSITION inputs:
- * d_input fp32 [P, pos_pad], pos_pad = in_pos rounded up to 64, columns >= in_pos are zero
+ * d_input fp32 [P, cols], cols = nmx_mlp_input_grad_cols(plan) >= in_pos, columns >= in_pos are zero
  * (= dY_0 W_0[:, :in_pos] + dY_skip W_skip[:, :in_pos]).  This is what lets a learnable encoder in front of the MLP
  * -- the hash grid (encoding/multi_hash.py) -- receive its gradient, as the reference's autograd would provide. */
 int nmx_mlp_bwd_input(nmx_mlp_plan* plan, void* workspace, const float* params, const float* d_out, float* d_params,
                       float* d_input, int64_t P, void* stream);
+/* row length of the d_input the NEXT nmx_mlp_bwd_input on this plan writes: in_pos rounded up to 64 on the per-layer /
+ * chain paths, exactly in_pos after a saving forward through the fused width-64 kernel (width 64, no view-dir head, no
+ * skip connection, in_pos 32 or 64, enc_kind 0), whose backward writes the compact gradient directly. */
+int nmx_mlp_input_grad_cols(const nmx_mlp_plan* plan);
 
 /* generic bf16 GEMM building block on tcgen05 (exposed for unit tests / profiling):
  * D[M,N] = act(A[M,K] * B[N,K]^T + bias[N]);  A,B bf16 row-major (K-major), D bf16 or fp32. */

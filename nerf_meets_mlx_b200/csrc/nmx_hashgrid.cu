@@ -7,8 +7,9 @@
 // Mapping: one thread per (point, level), level fastest.  The 16 lanes of a point share its 12-byte position
 // (one broadcast load), each lane gathers its level's 8 corners as vector loads of F floats (8 B for F=2), and
 // the [P, L*F] output row is written as one fully coalesced run per point.  Gradient scatter uses the
-// vectorised red.global.add.v2.f32 (atomicAdd(float2*)) so each corner costs one L2 atomic, after a warp-level
-// pre-reduction of lanes that hit the same table entry (coarse levels: a warp's points share corners).
+// vectorised red.global.add.v2.f32 / v4.f32 (atomicAdd(float2* / float4*)): one L2 atomic per corner, or per x edge when
+// its two corners share an aligned 16-byte slot; warps whose lanes share a cell (coarse levels, samples of one ray) first
+// merge lanes that hit the same table entry.
 // HBM/L2 roofline: fwd 1164 B/pt, bwd 2188 B/pt at L=16, F=2.
 #include "nmx_common.cuh"
 
@@ -82,6 +83,9 @@ hashgrid_fwd_kernel(const float* __restrict__ x, const float* __restrict__ table
     V hv[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) hv[k] = __ldg(tab + c.idx[k]);
+    // (Fetching the two corners of an x edge with one 16-byte load when they share an aligned slot -- x0 even, see the
+    // backward kernel -- was measured and is 7 % SLOWER here: 99 vs 91 us per 262 144 points; the extra selects cost
+    // more than the saved L1 requests.  The same pairing halves the atomics of the backward pass and stays there.)
     if (idx_out != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) idx_out[t * 8 + k] = (int32_t)c.idx[k];
@@ -164,6 +168,43 @@ hashgrid_bwd_kernel(const float* __restrict__ x, const float* __restrict__ res, 
       float wy[2] = {__fsub_rn(1.0f, c.oy), c.oy};
       float wz[2] = {__fsub_rn(1.0f, c.oz), c.oz};
       float* tab = d_tables + (size_t)l * T * F;
+      // One match on the CELL decides the path for the whole warp: when no two lanes sit in the same cell (random points,
+      // fine levels) the per-corner match / shuffle merging below cannot pay and is skipped.
+      const unsigned cell_peers = __match_any_sync(0xffffffffu, active ? c.idx[6] : 0xffffff00u + (unsigned)lane);
+      const bool solo = __all_sync(0xffffffffu, __popc(cell_peers) == 1);
+      if (solo) {
+        if constexpr (F == 2) {
+          // The two corners of an x edge hash to (x0 ^ A) and (x1 ^ A) (the x prime is 1): whenever x0 is even they are
+          // the two halves of one aligned 16-byte slot and take ONE 16-byte vector atomic instead of two 8-byte ones
+          const bool pair_ok = ((c.idx[3] ^ c.idx[0]) == 1u);
+          constexpr int ka[4] = {0, 1, 5, 4}, kb[4] = {3, 2, 6, 7};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float wa = wx[1] * wy[cys[kb[j]]] * wz[czs[kb[j]]], wb = wx[0] * wy[cys[kb[j]]] * wz[czs[kb[j]]];
+            if (!active) continue;
+            if (pair_ok) {
+              const bool b_hi = (c.idx[kb[j]] & 1u) != 0u;
+              const float wlo = b_hi ? wa : wb, whi = b_hi ? wb : wa;
+              atomicAdd(reinterpret_cast<float4*>(tab + (size_t)(c.idx[kb[j]] & ~1u) * 2),
+                        make_float4(wlo * g[0], wlo * g[1], whi * g[0], whi * g[1]));
+            } else {
+              atomicAdd(reinterpret_cast<float2*>(tab + (size_t)c.idx[ka[j]] * 2), make_float2(wa * g[0], wa * g[1]));
+              atomicAdd(reinterpret_cast<float2*>(tab + (size_t)c.idx[kb[j]] * 2), make_float2(wb * g[0], wb * g[1]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (!active) continue;
+            const float w = wx[cxs[k]] * wy[cys[k]] * wz[czs[k]];
+            float v[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[f] = w * g[f];
+            red_add<F>(tab + (size_t)c.idx[k] * F, v);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float w = active ? wx[cxs[k]] * wy[cys[k]] * wz[czs[k]] : 0.0f;

@@ -14,6 +14,7 @@
 
 #include "nmx_common.cuh"
 #include "nmx_gemm.cuh"
+#include "nmx_tiny.cuh"
 #include "nmx_chain.cuh"
 #include "nmx_sm100.cuh"
 
@@ -49,6 +50,7 @@ struct nmx_mlp_plan {
   // activation region (offsets relative to its start; depend on capacity)
   int64_t act_points_train, act_points_infer;
   int bits_word_major;  // layout of the sign-bit tiles written by the last saving forward (1 = pair kernel, word-major)
+  int last_fwd_tiny;    // the last saving forward ran the fused width-64 kernel (nmx_tiny.cu): only the bf16 input is saved
 };
 
 namespace {
@@ -522,6 +524,8 @@ extern "C" int nmx_mlp_plan_create(const nmx_mlp_config* c, int64_t max_points, 
   nmx_mlp_plan* p = new nmx_mlp_plan();
   p->cfg = *c;
   p->max_points = (max_points + 127) / 128 * 128;  // activation regions hold whole 128-point tiles
+  p->bits_word_major = 0;
+  p->last_fwd_tiny = 0;
   p->D = c->n_layers;
   p->W = c->width;
   p->in_pos = c->in_pos;
@@ -981,6 +985,30 @@ int forward_chain2_train(const Ctx& c, int64_t P, float* out, const EncIn& enc) 
 
 }  // namespace
 
+// ---- fused width-64 MLP (nmx_tiny.cu): nets without view-dir head or skip connection on an already-encoded input
+namespace {
+bool tiny_ok(const nmx_mlp_plan* p, int enc_kind) {
+  const bool off = getenv("NMX_DISABLE_TINY") != nullptr;  // read per call: the parity test runs both paths in one process
+  return !off && enc_kind == 0 && p->W == 64 && !p->cfg.use_viewdirs && p->cfg.skip_layer < 0 && p->D >= 1 &&
+         p->D <= kTinyMaxLayers && (p->in_pos == 32 || (p->in_pos == 64 && p->D <= 3)) && p->cfg.out_ch >= 1 &&
+         p->cfg.out_ch <= 8;
+}
+TinyMlpDesc tiny_desc(const nmx_mlp_plan* p, const float* params, int64_t P) {
+  TinyMlpDesc d;
+  memset(&d, 0, sizeof(d));
+  d.params = params;
+  for (int l = 0; l < p->D; ++l) { d.w_off[l] = p->trunk[l].w_off; d.b_off[l] = p->trunk[l].b_off; }
+  d.wo_off = p->outl.w_off; d.bo_off = p->outl.b_off;
+  d.D = p->D; d.in_pos = p->in_pos; d.out_ch = p->cfg.out_ch; d.P = P;
+  return d;
+}
+}  // namespace
+
+extern "C" int nmx_mlp_input_grad_cols(const nmx_mlp_plan* p) {
+  if (!p) return 0;
+  return p->last_fwd_tiny ? p->in_pos : p->pos_pad;
+}
+
 extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params, int enc_kind,
                            const float* x_or_rays, int ray_stride, const float* z, const float* bands, float* out,
                            int64_t B, int n, int save_activations, void* stream_) {
@@ -1001,6 +1029,16 @@ extern "C" int nmx_mlp_fwd(nmx_mlp_plan* p, void* workspace, const float* params
   const int out_cols = p->cfg.use_viewdirs ? 4 : p->cfg.out_ch;
   int rc;
   c.enc_kind = enc_kind;
+  if (c.training) p->last_fwd_tiny = 0;
+  if (tiny_ok(p, enc_kind)) {  // one launch, nothing but the bf16 input kept for the backward pass
+    bf16* x0_save = nullptr;
+    if (c.training) {
+      c.al = act_layout(p, p->max_points, true);
+      x0_save = c.X0();
+      p->last_fwd_tiny = 1;
+    }
+    return launch_tiny_fwd(tiny_desc(p, params, P), x_or_rays, out, x0_save, p->x0_cols, c.s);
+  }
   if (c.training) {
     c.al = act_layout(p, p->max_points, true);
     const bool pair_train = chain_eligible(p) && chain2t_ok(p, enc_kind, n, P);
@@ -1074,6 +1112,13 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
   cudaStream_t s = (cudaStream_t)stream_;
   NMX_CUDA(cudaMemsetAsync(d_params, 0, p->n_params * sizeof(float), s));
   if (P == 0) return 0;
+  if (p->last_fwd_tiny) {  // fused width-64 backward: d_input is [P, in_pos] (nmx_mlp_input_grad_cols)
+    Ctx c;
+    c.p = p; c.ws = (uint8_t*)workspace; c.params = params; c.s = s; c.training = true;
+    c.act = c.ws + p->weights_bytes + dirpe_bytes(p);
+    c.al = act_layout(p, p->max_points, true);
+    return launch_tiny_bwd(tiny_desc(p, params, P), c.X0(), p->x0_cols, d_out, d_params, d_input, s);
+  }
   Ctx c;
   c.p = p; c.ws = (uint8_t*)workspace; c.params = params; c.s = s; c.training = true;
   c.act = c.ws + p->weights_bytes + dirpe_bytes(p);

@@ -225,8 +225,8 @@ class NeRF(torch.nn.Module):
             return g
         # gradient w.r.t. the encoded position inputs [P, pos_pad] fp32; view-direction inputs get zeros (no learnable
         # encoder feeds them in the reference)
-        pos_pad = (self.channel_input_pos + 63) // 64 * 64
-        d_pad = torch.empty((P, pos_pad), dtype=torch.float32, device=g.device)
+        cols = int(L.lib().nmx_mlp_input_grad_cols(self._plan))  # in_pos (fused width-64 kernel) or in_pos padded to 64
+        d_pad = torch.empty((P, cols), dtype=torch.float32, device=g.device)
         L.call("nmx_mlp_bwd_input", self._plan, L.ptr(self._ws), L.ptr(self.flat), L.ptr(d_out), L.ptr(g), L.ptr(d_pad),
                L.i64(P), L.stream())
         d_x = d_pad[:, :self.channel_input_pos]

@@ -1,0 +1,92 @@
+"""Fused width-64 MLP (csrc/nmx_tiny.cu: register-resident mma.sync chain, in-kernel weight gradients) against
+  * the per-layer tcgen05 path of the same library on the same inputs (NMX_DISABLE_TINY=1 in the same process), and
+  * the torch restatement of NeRF.forward with bf16 rounding at the kernels' storage points (tests/test_mlp_gpu.py),
+including the gradient w.r.t. the encoded input (what the hash grid in front of it receives), ragged point counts
+(P % 16 != 0, P % 128 != 0, P = 1) and every (depth, input width) the kernel is instantiated for."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import models as omodels  # noqa: E402
+from test_mlp_gpu import emulated_forward, rel_max, rel_norm  # noqa: E402
+
+
+def _net(D, cin, cout, seed=3):
+    from nerf_meets_mlx_b200.models import NeRF
+    kw = dict(n_layers=D, width_layers=64, channel_input=cin, channel_input_views=0, channel_output=cout,
+              list_skip_connection_layers=[], is_use_view_directions=False)
+    ref = omodels.NeRF(seed=seed, **kw)
+    net = NeRF(device="cuda", max_points=8192, **kw)
+    net.load_reference_parameters(ref.params)
+    return ref, net
+
+
+def _run(net, x, g_out, fused):
+    """forward (saving) + backward incl. input gradient through the raw C-ABI calls, on the chosen path"""
+    if fused:
+        os.environ.pop("NMX_DISABLE_TINY", None)
+    else:
+        os.environ["NMX_DISABLE_TINY"] = "1"
+    try:
+        P = x.shape[0]
+        y = net._fwd_raw(0, x, None, None, P, 1, save=True).clone()
+        g, d_x = net._bwd_raw(g_out, P, want_input_grad=True)
+        with torch.no_grad():
+            y_inf = net._fwd_raw(0, x, None, None, P, 1, save=False).clone()
+        torch.cuda.synchronize()
+        return y, g.clone(), d_x.clone(), y_inf
+    finally:
+        os.environ.pop("NMX_DISABLE_TINY", None)
+
+
+CASES = [(1, 32, 1, 1), (2, 32, 4, 100), (2, 32, 4, 5000), (3, 64, 8, 1000), (4, 32, 3, 129), (1, 64, 3, 300),
+         (2, 64, 4, 2049), (3, 32, 5, 8192)]
+
+
+@pytest.mark.parametrize("D,cin,cout,P", CASES)
+def test_fused_tiny_mlp_matches_per_layer_path_and_emulated_reference(D, cin, cout, P, measured):
+    torch.manual_seed(D * 1000 + cin + P)
+    ref, net = _net(D, cin, cout)
+    x = torch.randn(P, cin).clamp(-1, 1)
+    g_out = torch.randn(P, cout)
+    xc, gc = x.cuda(), g_out.cuda()
+    y_f, g_f, dx_f, yi_f = _run(net, xc, gc, fused=True)
+    y_l, g_l, dx_l, _ = _run(net, xc, gc, fused=False)
+    assert dx_f.shape == (P, cin) and dx_l.shape == (P, cin)
+    assert torch.equal(y_f, yi_f)  # saving and non-saving forwards are the same arithmetic
+    # the two CUDA paths: same operand precision, different accumulation order
+    assert rel_max(y_f, y_l) < 2e-3
+    assert rel_norm(dx_f, dx_l) < 1e-2
+    got_f, got_l = net.split_flat(g_f), net.split_flat(g_l)
+    for n in got_f:
+        assert rel_norm(got_f[n], got_l[n]) < 1e-2, n
+    # torch reference with the kernels' bf16 storage points
+    xr = x.clone().requires_grad_(True)
+    ref.requires_grad_(True)
+    y_emu = emulated_forward(ref, xr)
+    names = list(ref.params.keys())
+    grads = torch.autograd.grad((y_emu * g_out).sum(), [ref.params[n] for n in names] + [xr])
+    assert rel_max(y_f.cpu(), y_emu.detach()) < 2e-3
+    for n, ge in zip(names, grads[:-1]):
+        e = measured(f"tiny_mlp_grad_vs_emulated/D{D}_in{cin}_P{P}", rel_norm(got_f[n].cpu(), ge))
+        assert e < 1e-2, f"grad {n}: {e}"
+    e = measured(f"tiny_mlp_input_grad_vs_emulated/D{D}_in{cin}_P{P}", rel_norm(dx_f.cpu(), grads[-1]))
+    assert e < 1e-2, f"input grad: {e}"
+    # fp32 oracle forward (north_star tolerance for bf16 MLP outputs)
+    assert rel_max(y_f.cpu(), ref.forward(x).detach()) < 1e-2
+
+
+def test_fused_tiny_mlp_backward_without_input_gradient_and_repeat():
+    """nmx_mlp_bwd (no d_input) takes the same kernel; a second backward on the same saved input gives the same gradient
+    up to the order of the fp32 atomics."""
+    torch.manual_seed(1)
+    ref, net = _net(2, 32, 4)
+    P = 3000
+    x, g_out = torch.randn(P, 32, device="cuda").clamp(-1, 1), torch.randn(P, 4, device="cuda")
+    net._fwd_raw(0, x, None, None, P, 1, save=True)
+    g0 = net._bwd_raw(g_out, P).clone()
+    g1, _ = net._bwd_raw(g_out, P, want_input_grad=True)
+    assert rel_norm(g0, g1) < 1e-5
