@@ -430,9 +430,11 @@ mlp_chain2_kernel(const __grid_constant__ Chain2Maps maps, const Chain2Params pr
 //    optionally stored as a bf16 [rays, 64] table (training: X0[:, 64:128] is filled from it), and the view-dir term of
 //    the dir layer out[b, o] = sum_k bf16(W_dir[o, W + k]) * PE(dir_b)[k] (fp32 accumulate, increasing k).  A block keeps
 //    the 27 x 128 bf16-rounded weight columns in shared memory and walks over rays.
+constexpr int kPrepWStride = 65;  // floats per output row of the staged view-dir weights (odd: conflict-free both ways)
+
 __global__ void __launch_bounds__(128)
 ray_prep_kernel(const RayPrep a) {
-  __shared__ float w_s[64 * 128];
+  __shared__ float w_s[128 * kPrepWStride];
   __shared__ float pe[2][64];
   const int o = threadIdx.x;
   {
@@ -451,8 +453,17 @@ ray_prep_kernel(const RayPrep a) {
     }
   }
   const int in_dir = 3 + 6 * a.n_freqs_dir;
-  const float* Wd = a.params + a.dir_w_off;
-  for (int k = 0; k < in_dir; ++k) w_s[k * 128 + o] = __bfloat162float(__float2bfloat16_rn(Wd[(size_t)o * a.dir_ldw + 256 + k]));
+  {  // stage W_dir[:, W:W+in_dir] (bf16-rounded): a warp reads one output row per step, lanes along k (coalesced), eight
+     // rows in flight (was one strided load per thread and k: 27 dependent round trips before the first ray)
+    const float* Wd = a.params + a.dir_w_off + 256;
+    const int lane = o & 31, warp = o >> 5;
+#pragma unroll 8
+    for (int r = warp; r < 128; r += 4) {
+      if (lane < in_dir) w_s[r * kPrepWStride + lane] = __bfloat162float(__float2bfloat16_rn(__ldg(Wd + (size_t)r * a.dir_ldw + lane)));
+      if (lane + 32 < in_dir)
+        w_s[r * kPrepWStride + lane + 32] = __bfloat162float(__float2bfloat16_rn(__ldg(Wd + (size_t)r * a.dir_ldw + lane + 32)));
+    }
+  }
   __nv_bfloat16* table = reinterpret_cast<__nv_bfloat16*>(a.dir_pe);
   int buf = 0;
   for (long long b = blockIdx.x; b < a.B; b += gridDim.x, buf ^= 1) {
@@ -471,9 +482,9 @@ ray_prep_kernel(const RayPrep a) {
       pe[buf][o] = __bfloat162float(vb);
       if (table != nullptr) table[b * 64 + o] = vb;
     }
-    __syncthreads();  // (double-buffered pe: one barrier per ray)
+    __syncthreads();  // (double-buffered pe: one barrier per ray; the first one also covers the staged weights)
     float acc = 0.0f;
-    for (int k = 0; k < in_dir; ++k) acc += w_s[k * 128 + o] * pe[buf][k];
+    for (int k = 0; k < in_dir; ++k) acc += w_s[o * kPrepWStride + k] * pe[buf][k];
     a.dir_bias[b * 128 + o] = acc;
   }
 }
@@ -484,7 +495,9 @@ namespace nmx {
 
 int launch_ray_prep(const RayPrep& rp, cudaStream_t stream) {
   if (rp.B <= 0) return 0;
-  long long blocks = rp.B < (long long)kNumSMs * 8 ? rp.B : (long long)kNumSMs * 8;
+  // ~8 rays per block amortise the 14 KB weight staging; at most 4 blocks per SM
+  long long blocks = (rp.B + 7) / 8;
+  if (blocks > (long long)kNumSMs * 4) blocks = (long long)kNumSMs * 4;
   if (blocks < 26) blocks = 26;  // the constants block is written 128 entries per block
   ray_prep_kernel<<<(unsigned)blocks, 128, 0, stream>>>(rp);
   NMX_LAUNCH_CHECK();

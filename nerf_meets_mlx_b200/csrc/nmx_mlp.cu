@@ -411,13 +411,26 @@ fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if ((int)blockIdx.x < tilesA) {  // dW_dir[o, j] += sum_k G[o,k] bf16(Wf[j,k]) + db_dir[o] bf[j]
     const int o0 = ((int)blockIdx.x / tiles_j) * 32, j0 = ((int)blockIdx.x % tiles_j) * 32;
+    float ra[4], rb[4];  // next K chunk, loaded while the current one is multiplied (the loop is latency-bound)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = G[(size_t)(o0 + ty * 4 + i) * W + tx];
+      rb[i] = Wf[(size_t)(j0 + ty * 4 + i) * W + tx];
+    }
     for (int k0 = 0; k0 < W; k0 += 32) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        sa[ty * 4 + i][tx] = G[(size_t)(o0 + ty * 4 + i) * W + k0 + tx];
-        sb[ty * 4 + i][tx] = bfr(Wf[(size_t)(j0 + ty * 4 + i) * W + k0 + tx]);
+        sa[ty * 4 + i][tx] = ra[i];
+        sb[ty * 4 + i][tx] = bfr(rb[i]);
       }
       __syncthreads();
+      if (k0 + 32 < W) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ra[i] = G[(size_t)(o0 + ty * 4 + i) * W + k0 + 32 + tx];
+          rb[i] = Wf[(size_t)(j0 + ty * 4 + i) * W + k0 + 32 + tx];
+        }
+      }
 #pragma unroll
       for (int kk = 0; kk < 32; ++kk) {
         const float w = sb[tx][kk];
@@ -435,13 +448,26 @@ fold_feature_grads_kernel(const float* __restrict__ G, const float* __restrict__
     const int t = (int)blockIdx.x - tilesA;
     const int j0 = (t / tiles_j) * 32, k0 = (t % tiles_j) * 32;
     float accb = 0.0f;
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ra[i] = Wd[(size_t)(ty * 4 + i) * ldwd + j0 + tx];
+      rb[i] = G[(size_t)(ty * 4 + i) * W + k0 + tx];
+    }
     for (int o0 = 0; o0 < Wh; o0 += 32) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        sa[ty * 4 + i][tx] = bfr(Wd[(size_t)(o0 + ty * 4 + i) * ldwd + j0 + tx]);
-        sb[ty * 4 + i][tx] = G[(size_t)(o0 + ty * 4 + i) * W + k0 + tx];
+        sa[ty * 4 + i][tx] = bfr(ra[i]);
+        sb[ty * 4 + i][tx] = rb[i];
       }
       __syncthreads();
+      if (o0 + 32 < Wh) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ra[i] = Wd[(size_t)(o0 + 32 + ty * 4 + i) * ldwd + j0 + tx];
+          rb[i] = G[(size_t)(o0 + 32 + ty * 4 + i) * W + k0 + tx];
+        }
+      }
 #pragma unroll
       for (int oo = 0; oo < 32; ++oo) {
         const float g = sb[oo][tx];
