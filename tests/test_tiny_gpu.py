@@ -14,12 +14,12 @@ from oracle import models as omodels  # noqa: E402
 from test_mlp_gpu import emulated_forward, rel_max, rel_norm  # noqa: E402
 
 
-def _net(D, cin, cout, seed=3):
+def _net(D, cin, cout, seed=3, max_points=8192):
     from nerf_meets_mlx_b200.models import NeRF
     kw = dict(n_layers=D, width_layers=64, channel_input=cin, channel_input_views=0, channel_output=cout,
               list_skip_connection_layers=[], is_use_view_directions=False)
     ref = omodels.NeRF(seed=seed, **kw)
-    net = NeRF(device="cuda", max_points=8192, **kw)
+    net = NeRF(device="cuda", max_points=max_points, **kw)
     net.load_reference_parameters(ref.params)
     return ref, net
 
@@ -43,13 +43,13 @@ def _run(net, x, g_out, fused):
 
 
 CASES = [(1, 32, 1, 1), (2, 32, 4, 100), (2, 32, 4, 5000), (3, 64, 8, 1000), (4, 32, 3, 129), (1, 64, 3, 300),
-         (2, 64, 4, 2049), (3, 32, 5, 8192)]
+         (2, 64, 4, 2049), (3, 32, 5, 8192), (2, 32, 4, 262144)]  # the last one: config C4's net at its BASELINE size
 
 
 @pytest.mark.parametrize("D,cin,cout,P", CASES)
 def test_fused_tiny_mlp_matches_per_layer_path_and_emulated_reference(D, cin, cout, P, measured):
     torch.manual_seed(D * 1000 + cin + P)
-    ref, net = _net(D, cin, cout)
+    ref, net = _net(D, cin, cout, max_points=max(P, 8192))
     x = torch.randn(P, cin).clamp(-1, 1)
     g_out = torch.randn(P, cout)
     xc, gc = x.cuda(), g_out.cuda()
@@ -73,6 +73,8 @@ def test_fused_tiny_mlp_matches_per_layer_path_and_emulated_reference(D, cin, co
     for n, ge in zip(names, grads[:-1]):
         e = measured(f"tiny_mlp_grad_vs_emulated/D{D}_in{cin}_P{P}", rel_norm(got_f[n].cpu(), ge))
         assert e < 1e-2, f"grad {n}: {e}"
+    # (the emulated reference rounds x through a bf16 TENSOR, so autograd rounds its input gradient to bf16 as well:
+    # the ~1.6e-3 measured here is that rounding, the weight gradients agree to <= 1e-4)
     e = measured(f"tiny_mlp_input_grad_vs_emulated/D{D}_in{cin}_P{P}", rel_norm(dx_f.cpu(), grads[-1]))
     assert e < 1e-2, f"input grad: {e}"
     # fp32 oracle forward (north_star tolerance for bf16 MLP outputs)
