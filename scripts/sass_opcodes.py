@@ -9,10 +9,11 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEY = ["UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTMAPF", "SYNCS", "REDG", "ATOMG", "RED", "ELECT",
-       "FADD2", "FFMA2", "F2FP", "MUFU", "HMMA", "STS", "LDS", "LDG", "STG", "MEMBAR", "FENCE", "CCTL"]
+       "FADD2", "FFMA2", "F2FP", "MUFU", "HMMA", "LDSM", "STS", "LDS", "LDG", "STG", "MEMBAR", "FENCE", "CCTL"]
 out = ["SASS opcode counts per object file (cuobjdump -sass of nerf_meets_mlx_b200/_lib/*.o, sm_100a).",
        "UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTMALDG/UTMASTG = cp.async.bulk.tensor load/store,",
-       "UBLKCP = cp.async.bulk, SYNCS = mbarrier, REDG = red.global (vector reductions of the weight-gradient flush).", ""]
+       "UBLKCP = cp.async.bulk, SYNCS = mbarrier, REDG = red.global (vector reductions of the weight-gradient flush).",
+       "HMMA / LDSM = mma.sync / ldmatrix: only in nmx_tiny.o, the byte-bound width-64 MLP (DESIGN.md 3.2).", ""]
 for o in sorted(glob.glob(os.path.join(ROOT, "nerf_meets_mlx_b200", "_lib", "*.o"))):
     txt = subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True).stdout
     ops = collections.Counter()
