@@ -55,13 +55,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* smem_row) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 
@@ -154,20 +153,28 @@ __device__ __forceinline__ void init_bias(float (&C)[8][4], const float* __restr
   }
 }
 
-// accumulator fragment -> ReLU -> bf16 A fragment of the next layer
+// accumulator fragment -> bf16 A fragment of the next layer, ReLU on the packed pair (round-to-bf16 is monotone and
+// keeps 0, so max(round(x), 0) == round(max(x, 0)))
+__device__ __forceinline__ uint32_t relu_pack2(float lo, float hi) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+  const __nv_bfloat162 v = __hmax2(__floats2bfloat162_rn(lo, hi), z);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ void relu_pack(const float (&C)[8][4], uint32_t (&A)[4][4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    A[j][0] = pack_bf16(fmaxf(C[2 * j][0], 0.0f), fmaxf(C[2 * j][1], 0.0f));
-    A[j][1] = pack_bf16(fmaxf(C[2 * j][2], 0.0f), fmaxf(C[2 * j][3], 0.0f));
-    A[j][2] = pack_bf16(fmaxf(C[2 * j + 1][0], 0.0f), fmaxf(C[2 * j + 1][1], 0.0f));
-    A[j][3] = pack_bf16(fmaxf(C[2 * j + 1][2], 0.0f), fmaxf(C[2 * j + 1][3], 0.0f));
+    A[j][0] = relu_pack2(C[2 * j][0], C[2 * j][1]);
+    A[j][1] = relu_pack2(C[2 * j][2], C[2 * j][3]);
+    A[j][2] = relu_pack2(C[2 * j + 1][0], C[2 * j + 1][1]);
+    A[j][3] = relu_pack2(C[2 * j + 1][2], C[2 * j + 1][3]);
   }
 }
 
-// data-gradient fragment: C * [h > 0] (h: bf16 A-fragment layout, post-ReLU so "> 0" is "bits != 0") -> bf16 A fragment
+// data-gradient fragment: C * [h > 0] (h: bf16 A-fragment layout, post-ReLU) -> bf16 A fragment; the mask is taken on
+// the packed pair (0xffff per half where h > 0)
 __device__ __forceinline__ uint32_t mask_pack2(float lo, float hi, uint32_t h) {
-  return pack_bf16((h & 0x7fffu) ? lo : 0.0f, (h & 0x7fff0000u) ? hi : 0.0f);
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+  return pack_bf16(lo, hi) & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&h), z);
 }
 __device__ __forceinline__ void mask_pack(const float (&C)[8][4], const uint32_t (&H)[4][4], uint32_t (&Y)[4][4]) {
 #pragma unroll
@@ -179,26 +186,23 @@ __device__ __forceinline__ void mask_pack(const float (&C)[8][4], const uint32_t
   }
 }
 
-// a warp's 16 rows of a [128][kTileStride] tile <-> its A fragment (4-byte accesses, conflict-free: bank = 4 g + tq)
-__device__ __forceinline__ void store_frag(bf16* tile, int wrow, int g, int tq, const uint32_t (&A)[4][4]) {
-  uint32_t* t = reinterpret_cast<uint32_t*>(tile);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    t[((wrow + g) * kTileStride + j * 16 + tq * 2) >> 1] = A[j][0];
-    t[((wrow + g + 8) * kTileStride + j * 16 + tq * 2) >> 1] = A[j][1];
-    t[((wrow + g) * kTileStride + j * 16 + 8 + tq * 2) >> 1] = A[j][2];
-    t[((wrow + g + 8) * kTileStride + j * 16 + 8 + tq * 2) >> 1] = A[j][3];
-  }
+// a warp's 16 rows of a [128][kTileStride] tile <-> its A fragment: A[j][0..3] are the four 8 x 8 blocks (rows 0-7 | 8-15)
+// x (columns 16j.. | 16j+8..), exactly the register layout of stmatrix / ldmatrix .x4; `frag_addr` is this lane's row
+// address for j = 0 (lane -> block lane/8, row lane%8), 144-byte row stride: conflict-free
+__device__ __forceinline__ uint32_t frag_addr(const bf16* tile, int wrow, int lane) {
+  return smem_addr(tile + (wrow + (lane & 7) + ((lane >> 3) & 1) * 8) * kTileStride + ((lane >> 4) & 1) * 8);
 }
-__device__ __forceinline__ void load_frag(const bf16* tile, int wrow, int g, int tq, uint32_t (&A)[4][4]) {
-  const uint32_t* t = reinterpret_cast<const uint32_t*>(tile);
+__device__ __forceinline__ void store_frag(uint32_t addr, const uint32_t (&A)[4][4]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    A[j][0] = t[((wrow + g) * kTileStride + j * 16 + tq * 2) >> 1];
-    A[j][1] = t[((wrow + g + 8) * kTileStride + j * 16 + tq * 2) >> 1];
-    A[j][2] = t[((wrow + g) * kTileStride + j * 16 + 8 + tq * 2) >> 1];
-    A[j][3] = t[((wrow + g + 8) * kTileStride + j * 16 + 8 + tq * 2) >> 1];
-  }
+  for (int j = 0; j < 4; ++j)
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr + j * 32), "r"(A[j][0]),
+                 "r"(A[j][1]), "r"(A[j][2]), "r"(A[j][3]) : "memory");
+}
+__device__ __forceinline__ void load_frag(uint32_t addr, uint32_t (&A)[4][4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(A[j][0]), "=r"(A[j][1]), "=r"(A[j][2]), "=r"(A[j][3]) : "r"(addr + j * 32) : "memory");
 }
 
 template <int D, int KIN>
@@ -311,7 +315,7 @@ struct BwdSmem {
   static constexpr int wbh = wb0 + 4 * (KIN / 8) * 64;
   static constexpr int bias = wbh + (D - 1) * 2048;
   static constexpr int wo = bias + D * 64;                        // head fragments, hi + lo (pack_head_bwd)
-  static constexpr int t_do = wo + 512;                           // fp32 [128][8]
+  static constexpr int t_do = wo + 512;                           // d_out as bf16 hi | lo, [2][128][8]
   static constexpr int t_x0 = t_do + 128 * 8;                     // bf16 [128][KIN + 8]
   static constexpr int t_h = t_x0 + 128 * x0_stride / 2;          // bf16 [D][128][72]
   static constexpr int t_dy = t_h + D * 128 * kTileStride / 2;    // bf16 [D][128][72]
@@ -331,7 +335,7 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
   uint32_t* wbh = smem_u32 + S::wbh;
   float* bias = reinterpret_cast<float*>(smem_u32 + S::bias);
   uint32_t* wo = smem_u32 + S::wo;
-  float* t_do = reinterpret_cast<float*>(smem_u32 + S::t_do);
+  bf16* t_do = reinterpret_cast<bf16*>(smem_u32 + S::t_do);  // [0]: hi, [1024 elements on]: lo
   bf16* t_x0 = reinterpret_cast<bf16*>(smem_u32 + S::t_x0);
   bf16* t_h = reinterpret_cast<bf16*>(smem_u32 + S::t_h);
   bf16* t_dy = reinterpret_cast<bf16*>(smem_u32 + S::t_dy);
@@ -355,7 +359,7 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
   const int wrow = warp * 16;
   const int mt = warp & 3, hh = warp >> 2;  // weight-gradient block of this warp: dW rows mt*16.., column half hh
   constexpr int NTW0 = KIN / 16;            // n-tiles per warp, layer 0 (input columns) / hidden layers: 4
-  float accW0[NTW0][4], accWh[D > 1 ? D - 1 : 1][4][4], accB[D][4], accO[4], accOb[4];
+  float accW0[NTW0][4], accWh[D > 1 ? D - 1 : 1][4][4], accB[D][4], accO[4], dbo[2] = {0.0f, 0.0f};
 #pragma unroll
   for (int q = 0; q < NTW0; ++q)
 #pragma unroll
@@ -371,7 +375,18 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
 #pragma unroll
     for (int e = 0; e < 4; ++e) accB[l][e] = 0.0f;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) accO[e] = accOb[e] = 0.0f;
+  for (int e = 0; e < 4; ++e) accO[e] = 0.0f;
+
+  // phase-2 operand addresses (32-bit shared-memory byte addresses of this lane's ldmatrix rows at k-step 0):
+  //   A = dY_l^T: matrices (points 0-7 | 8-15) x (o 0-7 | 8-15) of the warp's 16 rows mt*16..;  B = X_l: two n-tiles per x4
+  const int a_row = (lane & 7) + ((lane >> 4) & 1) * 8, a_col = mt * 16 + ((lane >> 3) & 1) * 8;
+  const int b_row = (lane & 7) + ((lane >> 3) & 1) * 8, b_col = ((lane >> 4) & 1) * 8;
+  const uint32_t sm_a = smem_addr(t_dy + a_row * kTileStride + a_col);
+  const uint32_t sm_b0 = smem_addr(t_x0 + b_row * S::x0_stride + hh * NTW0 * 8 + b_col);
+  const uint32_t sm_bh = smem_addr(t_h + b_row * kTileStride + hh * 32 + b_col);
+  const uint32_t sm_hl = smem_addr(t_h + (D - 1) * kTile + a_row * kTileStride + a_col);  // A = h_{D-1}^T, rows mt*16..
+  const uint32_t sm_do = smem_addr(t_do + hh * 1024 + b_row * 8);  // B = d_out (hi for warps 0-3, lo for warps 4-7)
+  const uint32_t sm_fh = frag_addr(t_h, wrow, lane), sm_fy = frag_addr(t_dy, wrow, lane);  // phase-1 fragment rows
 
   const int64_t P = a.P, n_tiles = (P + 127) >> 7;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -404,28 +419,32 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
     const float da1 = (va && o0 + 1 < a.out_ch) ? __ldg(d_out + ra * a.out_ch + o0 + 1) : 0.0f;
     const float db0 = (vb && o0 < a.out_ch) ? __ldg(d_out + rb * a.out_ch + o0) : 0.0f;
     const float db1 = (vb && o0 + 1 < a.out_ch) ? __ldg(d_out + rb * a.out_ch + o0 + 1) : 0.0f;
-    *reinterpret_cast<float2*>(t_do + (wrow + g) * 8 + o0) = make_float2(da0, da1);
-    *reinterpret_cast<float2*>(t_do + (wrow + g + 8) * 8 + o0) = make_float2(db0, db1);
+    dbo[0] += da0 + db0;  // db_out[o] = sum_p d_out[p][o]: this lane's two rows, channels tq*2, tq*2+1
+    dbo[1] += da1 + db1;
+    uint32_t dhi[4], dlo[4];  // bf16 hi + lo of d_out: A fragment of the head's data gradient, and (through the
+    split_pair(da0, da1, dhi[0], dlo[0]);  // shared-memory tiles) the transposed operand of its weight gradient
+    split_pair(db0, db1, dhi[1], dlo[1]);
+    dhi[2] = dhi[3] = dlo[2] = dlo[3] = 0u;
+    *reinterpret_cast<uint32_t*>(t_do + (wrow + g) * 8 + o0) = dhi[0];
+    *reinterpret_cast<uint32_t*>(t_do + (wrow + g + 8) * 8 + o0) = dhi[1];
+    *reinterpret_cast<uint32_t*>(t_do + 1024 + (wrow + g) * 8 + o0) = dlo[0];
+    *reinterpret_cast<uint32_t*>(t_do + 1024 + (wrow + g + 8) * 8 + o0) = dlo[1];
     float C[8][4];
     // recompute h_0 .. h_{D-1} (kept in the shared-memory tiles: ReLU masks and weight-gradient operands)
     init_bias(C, bias, tq);
     mma_layer<KIN / 16, 8>(C, A, wf0, lane);
     relu_pack(C, A);
-    store_frag(t_h, wrow, g, tq, A);
+    store_frag(sm_fh, A);
 #pragma unroll
     for (int l = 1; l < D; ++l) {
       init_bias(C, bias + l * 64, tq);
       mma_layer<4, 8>(C, A, wfh + (l - 1) * 2048, lane);
       relu_pack(C, A);
-      store_frag(t_h + l * kTile, wrow, g, tq, A);
+      store_frag(sm_fh + l * kTile * 2, A);
     }
     // dY_{D-1} = (d_out W_out) * [h_{D-1} > 0]: d_out and W_out as bf16 hi + lo, three MMAs per n-tile (the lo * lo term
     // is below fp32 rounding); A still holds h_{D-1}
     {
-      uint32_t dhi[4], dlo[4];
-      split_pair(da0, da1, dhi[0], dlo[0]);
-      split_pair(db0, db1, dhi[1], dlo[1]);
-      dhi[2] = dhi[3] = dlo[2] = dlo[3] = 0u;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const uint2 w = *reinterpret_cast<const uint2*>(wo + (nt * 32 + lane) * 2);
@@ -437,15 +456,15 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
     }
     uint32_t Y[4][4];
     mask_pack(C, A, Y);
-    store_frag(t_dy + (D - 1) * kTile, wrow, g, tq, Y);
+    store_frag(sm_fy + (D - 1) * kTile * 2, Y);
 #pragma unroll
     for (int l = D - 1; l >= 1; --l) {  // dY_{l-1} = (dY_l W_l) * [h_{l-1} > 0]
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) C[nt][0] = C[nt][1] = C[nt][2] = C[nt][3] = 0.0f;
       mma_layer<4, 8>(C, Y, wbh + (l - 1) * 2048, lane);
-      load_frag(t_h + (l - 1) * kTile, wrow, g, tq, A);
+      load_frag(sm_fh + (l - 1) * kTile * 2, A);
       mask_pack(C, A, Y);
-      store_frag(t_dy + (l - 1) * kTile, wrow, g, tq, Y);
+      store_frag(sm_fy + (l - 1) * kTile * 2, Y);
     }
     if (d_in != nullptr) {  // d_x = dY_0 W_0: a lane's 8 output columns of a 32-column block are contiguous
 #pragma unroll
@@ -469,56 +488,39 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
     // ---------------------------------------------------------------- phase 2: weight gradients of the 128 points
     // dW_l[o][i] += sum_p dY_l[p][o] X_l[p][i]: A = dY_l^T and B = X_l both come out of the [point][column] tiles
     // through ldmatrix.trans; this warp owns rows mt*16.. and a half of the columns.
-    const int a_row = (lane & 7) + ((lane >> 4) & 1) * 8, a_col = mt * 16 + ((lane >> 3) & 1) * 8;
-    const int b_row = (lane & 7) + ((lane >> 3) & 1) * 8, b_col = ((lane >> 4) & 1) * 8;
+    // One fully unrolled loop over the 8 k-steps (16 points each) carries every product -- ten independent accumulator
+    // chains per warp, so no MMA waits for its predecessor -- with all shared-memory addresses as base + immediate.
 #pragma unroll
-    for (int l = 0; l < D; ++l) {
-      const bf16* tA = t_dy + l * kTile;
-#pragma unroll 2
-      for (int ks = 0; ks < 8; ++ks) {
+    for (int ks = 0; ks < 8; ++ks) {
+      {  // output head, transposed: dW_out^T[c][o] += sum_p h_{D-1}[p][c] d_out[p][o] with A = h^T (rows mt*16..) and
+         // B = d_out as bf16 hi (warps 0-3) or lo (warps 4-7): the two halves add up to an fp32-grade product
+        uint32_t ah[4], bd[2];
+        ldmatrix_x4_trans(ah, sm_hl + ks * 16 * kTileStride * 2);
+        ldmatrix_x2_trans(bd, sm_do + ks * 16 * 16);
+        mma16816(accO, ah, bd[0], bd[1]);
+      }
+#pragma unroll
+      for (int l = 0; l < D; ++l) {
         uint32_t af[4];
-        ldmatrix_x4_trans(af, tA + (ks * 16 + a_row) * kTileStride + a_col);
+        ldmatrix_x4_trans(af, sm_a + (l * kTile + ks * 16 * kTileStride) * 2);
         if (l == 0) {
 #pragma unroll
           for (int q = 0; q < NTW0 / 2; ++q) {
             uint32_t bf[4];
-            ldmatrix_x4_trans(bf, t_x0 + (ks * 16 + b_row) * S::x0_stride + (hh * NTW0 + 2 * q) * 8 + b_col);
+            ldmatrix_x4_trans(bf, sm_b0 + (ks * 16 * S::x0_stride + 2 * q * 8) * 2);
             mma16816(accW0[2 * q], af, bf[0], bf[1]);
             mma16816(accW0[2 * q + 1], af, bf[2], bf[3]);
           }
         } else {
-          const bf16* tB = t_h + (l - 1) * kTile;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t bf[4];
-            ldmatrix_x4_trans(bf, tB + (ks * 16 + b_row) * kTileStride + (hh * 4 + 2 * q) * 8 + b_col);
+            ldmatrix_x4_trans(bf, sm_bh + ((l - 1) * kTile + ks * 16 * kTileStride + 2 * q * 8) * 2);
             mma16816(accWh[l > 0 ? l - 1 : 0][2 * q], af, bf[0], bf[1]);
             mma16816(accWh[l > 0 ? l - 1 : 0][2 * q + 1], af, bf[2], bf[3]);
           }
         }
-        if (hh == 0) mma16816(accB[l], af, kOnes, kOnes);  // db_l[o] = sum_p dY_l[p][o]
-      }
-    }
-    {  // output head: dW_out[o][c] += sum_p d_out[p][o] h_{D-1}[p][c], d_out as hi + lo bf16 (fp32-grade product);
-       // warp w owns columns w*8 .. w*8+7
-      const bf16* tB = t_h + (D - 1) * kTile;
-#pragma unroll 2
-      for (int ks = 0; ks < 8; ++ks) {
-        const int p0 = ks * 16 + tq * 2;
-        const float d00 = t_do[p0 * 8 + g], d01 = t_do[(p0 + 1) * 8 + g];
-        const float d80 = t_do[(p0 + 8) * 8 + g], d81 = t_do[(p0 + 9) * 8 + g];
-        uint32_t hi[4], lo[4];
-        hi[0] = pack_bf16(d00, d01); hi[2] = pack_bf16(d80, d81); hi[1] = hi[3] = 0u;
-        const float2 h0 = unpack_bf16(hi[0]), h2 = unpack_bf16(hi[2]);
-        lo[0] = pack_bf16(d00 - h0.x, d01 - h0.y); lo[2] = pack_bf16(d80 - h2.x, d81 - h2.y); lo[1] = lo[3] = 0u;
-        uint32_t bh[2];
-        ldmatrix_x2_trans(bh, tB + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kTileStride + warp * 8);
-        mma16816(accO, hi, bh[0], bh[1]);
-        mma16816(accO, lo, bh[0], bh[1]);
-        if (warp == 0) {
-          mma16816(accOb, hi, kOnes, kOnes);
-          mma16816(accOb, lo, kOnes, kOnes);
-        }
+        mma16816(accB[l], af, kOnes, kOnes);  // db_l[o] = sum_p dY_l[p][o] (both column halves compute it: no branch)
       }
     }
     __syncthreads();
@@ -551,9 +553,19 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
         atomicAdd(d_params + a.b_off[l] + mt * 16 + g + 8, accB[l][2]);
       }
     }
-    if (g < a.out_ch) {
-      atomicAdd(reinterpret_cast<float2*>(d_params + a.wo_off + g * 64 + warp * 8 + tq * 2), make_float2(accO[0], accO[1]));
-      if (warp == 0 && tq == 0) atomicAdd(d_params + a.bo_off + g, accOb[0]);
+    {  // head: accO = dW_out^T[c = mt*16 + g (+8)][o = tq*2 (+1)], hi and lo halves both add in
+      const int o0 = tq * 2, c0 = mt * 16 + g;
+      float* dWo = d_params + a.wo_off;
+      if (o0 < a.out_ch) { atomicAdd(dWo + o0 * 64 + c0, accO[0]); atomicAdd(dWo + o0 * 64 + c0 + 8, accO[2]); }
+      if (o0 + 1 < a.out_ch) { atomicAdd(dWo + (o0 + 1) * 64 + c0, accO[1]); atomicAdd(dWo + (o0 + 1) * 64 + c0 + 8, accO[3]); }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {  // db_out: sum this lane's partial over the 8 row groups of the warp
+        float v = dbo[e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0 && o0 + e < a.out_ch) atomicAdd(d_params + a.bo_off + o0 + e, v);
+      }
     }
   }
 }
