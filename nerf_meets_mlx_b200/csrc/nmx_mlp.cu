@@ -1285,7 +1285,9 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
       static int64_t batch_max_points = -1;
       if (batch_max_points < 0) {
         const char* e = getenv("NMX_WGRAD_BATCH_MAX_POINTS");
-        batch_max_points = e ? atoll(e) : 200000;  // measured on B200: faster up to ~200 k points, slower from ~400 k
+        // measured on B200: faster up to a 262 144-point pass (C2: 1.286 -> 1.272 ms), slower at 524 288 (C3 coarse pass:
+        // 9.85 -> 9.88 ms per step) and beyond
+        batch_max_points = e ? atoll(e) : 300000;
         if (getenv("NMX_DISABLE_WGRAD_BATCH")) batch_max_points = 0;
       }
       const bool batched = dual_ok && K == 1 && P <= batch_max_points && p->D + 1 <= kMaxWgradJobs;
@@ -1378,7 +1380,7 @@ static int mlp_bwd_impl(nmx_mlp_plan* p, void* workspace, const float* params, c
   static int64_t noview_batch_max = -1;  // same cross-over as the chain path's batched launch
   if (noview_batch_max < 0) {
     const char* e = getenv("NMX_WGRAD_BATCH_MAX_POINTS");
-    noview_batch_max = getenv("NMX_DISABLE_WGRAD_BATCH") ? 0 : (e ? atoll(e) : 200000);
+    noview_batch_max = getenv("NMX_DISABLE_WGRAD_BATCH") ? 0 : (e ? atoll(e) : 300000);
   }
   if (!p->cfg.use_viewdirs && P <= noview_batch_max && l2_rows == 0 && p->D <= kMaxWgradJobs) {
     // Nets without a view-dir head (image learning, the hash grid's tiny MLP), layer by layer: the data-gradient GEMMs
