@@ -64,6 +64,10 @@ int nmx_assemble_rays(const float* rays_o, const float* rays_d, int64_t B, float
 /* Embedder.embed (models/embedding.py:35-71): [x, sin(f0 x), cos(f0 x), ...], f_k = k^2 (reference quirk).
  * x: [P, in_dim] -> out: [P, (include_input?in_dim:0) + 2*in_dim*n_freqs] */
 int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n_freqs, int include_input, void* stream);
+/* the same with explicit frequency bands [n_freqs] fp32 on device (an Embedder built with max_freq_log2 != num_freqs - 1,
+ * models/embedding.py:44-49: bands = linspace(0, max_freq_log2, num_freqs) ** 2); bands == NULL: f_k = k^2 */
+int nmx_pe_embedder_bands_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim, int n_freqs,
+                              int include_input, void* stream);
 /* SinusoidalEncoding.__call__ (encoding/sinusoidal.py:39-66): sin([s, s + fp32(pi/2)]), s = x[:,d]*bands[k]
  * (dim-major, freq-minor); optional input appended at the end.  bands: [n_freqs] fp32 on device. */
 int nmx_pe_sinusoidal_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim, int n_freqs,

@@ -149,7 +149,8 @@ extern "C" int nmx_ray_points_fwd(const float* rays, int ray_stride, const float
 // independent range reductions in flight per thread, no 64-bit index division per element.
 constexpr int kPeTile = 32;
 __global__ void __launch_bounds__(256)
-pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t P, int in_dim, int n_freqs, int inc) {
+pe_embedder_kernel(const float* __restrict__ x, const float* __restrict__ bands, float* __restrict__ out, int64_t P, int in_dim,
+                   int n_freqs, int inc) {
   extern __shared__ float s_rows[];
   const int out_dim = inc + 2 * in_dim * n_freqs;
   const int items = in_dim * n_freqs;
@@ -166,7 +167,7 @@ pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t
     for (int i = threadIdx.x; i < np * items; i += 256) {
       const int pt = i / items, q = i - pt * items;
       const int k = q / in_dim, d = q - k * in_dim;
-      const float a = __fmul_rn(s_x[pt * in_dim + d], (float)(k * k));
+      const float a = __fmul_rn(s_x[pt * in_dim + d], bands != nullptr ? __ldg(bands + k) : (float)(k * k));
       float sv, cv;
       sincosf(a, &sv, &cv);
       float* row = s_rows + pt * out_dim + inc + k * 2 * in_dim;
@@ -180,8 +181,8 @@ pe_embedder_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t
   }
 }
 
-extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n_freqs, int include_input,
-                                   void* stream) {
+extern "C" int nmx_pe_embedder_bands_fwd(const float* x, const float* bands, float* out, int64_t P, int in_dim, int n_freqs,
+                                         int include_input, void* stream) {
   NMX_CHECK_ARG(P >= 0 && in_dim >= 1 && n_freqs >= 0, "P >= 0, in_dim >= 1, n_freqs >= 0");
   if (P == 0) return 0;
   int inc = include_input ? in_dim : 0;
@@ -190,9 +191,14 @@ extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in
   NMX_CHECK_ARG(out_dim <= 1024, "encoded width <= 1024");
   const size_t smem = (size_t)kPeTile * (out_dim + in_dim) * sizeof(float);
   if (smem > 48 * 1024) NMX_CUDA(cudaFuncSetAttribute(pe_embedder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pe_embedder_kernel<<<grid_for(P, kPeTile, 16), 256, smem, (cudaStream_t)stream>>>(x, out, P, in_dim, n_freqs, inc);
+  pe_embedder_kernel<<<grid_for(P, kPeTile, 16), 256, smem, (cudaStream_t)stream>>>(x, bands, out, P, in_dim, n_freqs, inc);
   NMX_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int nmx_pe_embedder_fwd(const float* x, float* out, int64_t P, int in_dim, int n_freqs, int include_input,
+                                   void* stream) {
+  return nmx_pe_embedder_bands_fwd(x, nullptr, out, P, in_dim, n_freqs, include_input, stream);
 }
 
 // K2b: SinusoidalEncoding (encoding/sinusoidal.py:49-66).  out[c]:

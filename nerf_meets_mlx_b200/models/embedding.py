@@ -32,12 +32,16 @@ class Embedder:
         if not self.kwargs["log_sampling"]:
             raise NotImplementedError  # embedding.py:50-51
         max_freq = self.kwargs["max_freq_log2"]
+        # get_embedder's choice max_freq_log2 = N - 1 gives the bands k^2 the kernels generate themselves (and the only
+        # ones the fused chain input encoder knows); any other value goes to the stand-alone kernel with explicit bands
+        self.bands = None
         if self.n_freqs > 1 and float(max_freq) != float(self.n_freqs - 1):
-            raise NotImplementedError("the fused kernels implement the reference's get_embedder bands (k^2, k < N)")
+            from ..encoding.sinusoidal import mlx_linspace
+            self.bands = mlx_linspace(0.0, float(max_freq), self.n_freqs) ** 2.0  # embedding.py:47-49
         self.out_dim = (in_dim if self.include_input else 0) + in_dim * 2 * self.n_freqs
 
     def embed(self, inputs):
-        return ops.pe_embedder(inputs, self.n_freqs, include_input=self.include_input)
+        return ops.pe_embedder(inputs, self.n_freqs, include_input=self.include_input, bands=self.bands)
 
 
 class _Identity:

@@ -102,14 +102,22 @@ def gen_rays(H, W, K, c2w, pix=None, near=0.0, far=1.0, n_cols=11, image=None):
 
 
 # ----------------------------------------------------------------------------------------- encodings
-def pe_embedder(x, n_freqs, include_input=True):
+def pe_embedder(x, n_freqs, include_input=True, bands=None):
+    """bands: optional [n_freqs] fp32 frequencies (default: the reference's get_embedder bands k^2)"""
     x = _f32c(x)
     require_cuda(x)
     in_dim = x.shape[-1]
     P = x.numel() // in_dim
     out_dim = (in_dim if include_input else 0) + 2 * in_dim * n_freqs
     out = torch.empty((P, out_dim), dtype=torch.float32, device=x.device)
-    call("nmx_pe_embedder_fwd", ptr(x), ptr(out), i64(P), i32(in_dim), i32(n_freqs), i32(1 if include_input else 0), stream())
+    if bands is None:
+        call("nmx_pe_embedder_fwd", ptr(x), ptr(out), i64(P), i32(in_dim), i32(n_freqs), i32(1 if include_input else 0),
+             stream())
+    else:
+        bands = _f32c(bands).to(x.device)
+        assert bands.numel() == n_freqs, "bands must hold n_freqs values"
+        call("nmx_pe_embedder_bands_fwd", ptr(x), ptr(bands), ptr(out), i64(P), i32(in_dim), i32(n_freqs),
+             i32(1 if include_input else 0), stream())
     return out.reshape(*x.shape[:-1], out_dim)
 
 

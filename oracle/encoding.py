@@ -15,10 +15,12 @@ F32 = np.float32
 
 
 # ----------------------------------------------------------------------------- PE flavour A
-def embedder_freq_bands(n_freqs):
-    """embedding.py:47-49: linspace(0, max_freq_log2=n_freqs-1, n_freqs) ** 2.0 -- SQUARES
-    [0,1,4,9,...], not powers of two (reference quirk, replicated)."""
-    return (linspace_mlx(0.0, n_freqs - 1, n_freqs) ** F32(2.0)).astype(F32)
+def embedder_freq_bands(n_freqs, max_freq_log2=None):
+    """embedding.py:47-49: linspace(0, max_freq_log2, n_freqs) ** 2.0 -- SQUARES; with get_embedder's
+    max_freq_log2 = n_freqs - 1 (embedding.py:81, the default here): [0,1,4,9,...], not powers of two (reference quirk,
+    replicated)."""
+    hi = n_freqs - 1 if max_freq_log2 is None else max_freq_log2
+    return (linspace_mlx(0.0, hi, n_freqs) ** F32(2.0)).astype(F32)
 
 
 def embedder_out_dim(n_freqs, n_input_dims=3):
@@ -28,15 +30,16 @@ def embedder_out_dim(n_freqs, n_input_dims=3):
     return include + n_input_dims * 2 * n_freqs
 
 
-def embedder_embed(x, n_freqs, n_input_dims=3):
-    """Embedder.embed (embedding.py:65-71): [x, sin(f0 x), cos(f0 x), sin(f1 x), cos(f1 x), ...]."""
+def embedder_embed(x, n_freqs, n_input_dims=3, max_freq_log2=None, include_input=None):
+    """Embedder.embed (embedding.py:65-71): [x, sin(f0 x), cos(f0 x), sin(f1 x), cos(f1 x), ...].  include_input defaults
+    to get_embedder's choice (embedding.py:79: off for 2-D inputs)."""
     x = np.asarray(x, dtype=F32)
     if n_freqs == -1:
         return x
     outs = []
-    if n_input_dims != 2:
+    if (n_input_dims != 2) if include_input is None else include_input:
         outs.append(x)
-    for f in embedder_freq_bands(n_freqs):
+    for f in embedder_freq_bands(n_freqs, max_freq_log2):
         xf = (x * f).astype(F32)
         outs.append(np.sin(xf).astype(F32))
         outs.append(np.cos(xf).astype(F32))

@@ -363,5 +363,35 @@ def main():
     print("golden vectors written to", OUT)
 
 
+def embedder_bands_golden():
+    """Embedder built directly with max_freq_log2 != num_freqs - 1 (models/embedding.py:23-71): bands
+    linspace(0, max_freq_log2, N) ** 2.  Own seed and own file, so the vectors above do not move:
+        python oracle/make_golden.py --embedder-bands"""
+    sys.path.insert(0, os.path.join(HERE, "mlx_shim"))
+    sys.path.insert(0, REF)
+    import mlx.core as mx
+    from mlx_nerf.models import embedding
+    rng = np.random.default_rng(20261019)
+    x3 = rng.uniform(-2.0, 2.0, size=(37, 3)).astype(np.float32)
+    x2 = rng.uniform(-1.0, 1.0, size=(19, 2)).astype(np.float32)
+    out = {"x3": x3, "x2": x2}
+    for tag, x, kw in (("a", x3, dict(include_input=True, input_dims=3, max_freq_log2=5.0, num_freqs=4)),
+                       ("b", x3, dict(include_input=False, input_dims=3, max_freq_log2=2.5, num_freqs=7)),
+                       ("c", x2, dict(include_input=True, input_dims=2, max_freq_log2=9, num_freqs=6)),
+                       ("d", x3, dict(include_input=True, input_dims=3, max_freq_log2=3.0, num_freqs=1))):
+        e = embedding.Embedder(log_sampling=True, periodic_funcs=[mx.sin, mx.cos], **kw)
+        out[f"{tag}_out"] = np.asarray(e.embed(x), dtype=np.float32)
+        out[f"{tag}_dim"] = e.out_dim
+        out[f"{tag}_max"] = float(kw["max_freq_log2"])
+        out[f"{tag}_n"] = kw["num_freqs"]
+        out[f"{tag}_inc"] = int(bool(kw["include_input"]))
+    np.savez_compressed(os.path.join(OUT, "pe_embedder_bands.npz"), **out)
+    print("written", os.path.join(OUT, "pe_embedder_bands.npz"))
+
+
 if __name__ == "__main__":
-    main()
+    if "--embedder-bands" in sys.argv:
+        embedder_bands_golden()
+    else:
+        main()
+        embedder_bands_golden()

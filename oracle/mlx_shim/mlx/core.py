@@ -50,6 +50,8 @@ def compile(fn=None, inputs=None, outputs=None):
 
 
 def linspace(start, stop, num=50, dtype=float32):
+    if num == 1:  # mx.linspace(a, b, num=1) is [a]
+        return _np.array([start], dtype=_np.float32).astype(dtype)
     seq = _np.arange(num, dtype=_np.float32)
     step = _np.float32((float(stop) - float(start)) / (num - 1))
     return (seq * step + _np.float32(start)).astype(dtype)

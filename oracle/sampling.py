@@ -10,6 +10,8 @@ F32 = np.float32
 
 def linspace_mlx(start, stop, num):
     """mx.linspace as assumed for MLX 0.7.0: arange(num)*step + start, all fp32 (third-party)."""
+    if num == 1:  # mx.linspace(a, b, num=1) is [a]
+        return np.array([start], dtype=F32)
     seq = np.arange(num, dtype=F32)
     step = F32((float(stop) - float(start)) / (num - 1))
     return seq * step + F32(start)

@@ -56,6 +56,18 @@ def test_pe_embedder_golden(ops, golden):
     np.testing.assert_allclose(out, g["pe_xy"], rtol=0, atol=2e-6)
 
 
+def test_pe_embedder_explicit_bands_golden(ops, golden):
+    """The mirrored Embedder class with max_freq_log2 != num_freqs - 1: explicit bands through nmx_pe_embedder_bands_fwd."""
+    from nerf_meets_mlx_b200.models.embedding import Embedder
+    g = golden("pe_embedder_bands")
+    for tag, x in (("a", "x3"), ("b", "x3"), ("c", "x2"), ("d", "x3")):
+        e = Embedder(include_input=bool(int(g[f"{tag}_inc"])), input_dims=g[x].shape[-1], max_freq_log2=float(g[f"{tag}_max"]),
+                     num_freqs=int(g[f"{tag}_n"]), log_sampling=True, periodic_funcs=["sin", "cos"])
+        assert e.out_dim == int(g[f"{tag}_dim"])
+        out = e.embed(dev(g[x])).cpu().numpy()
+        np.testing.assert_allclose(out, g[f"{tag}_out"], rtol=0, atol=2e-6)
+
+
 def test_pe_sinusoidal_golden(ops, golden):
     g = golden("pe_sinusoidal")
     bands = oenc.sinusoidal_freq_bands(10, 0.0, 8.0)

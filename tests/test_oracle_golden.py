@@ -66,6 +66,17 @@ def test_pe_embedder(golden):
     np.testing.assert_array_equal(oenc.embedder_freq_bands(10), np.arange(10, dtype=np.float32) ** 2)
 
 
+def test_pe_embedder_explicit_bands(golden):
+    """Embedder built directly with max_freq_log2 != num_freqs - 1 (bands linspace(0, max, N) ** 2), num_freqs = 1
+    included (mx.linspace(.., num=1) = [start]): the reference class run through the MLX stand-in."""
+    g = golden("pe_embedder_bands")
+    for tag, x in (("a", "x3"), ("b", "x3"), ("c", "x2"), ("d", "x3")):
+        n, mx_, inc = int(g[f"{tag}_n"]), float(g[f"{tag}_max"]), bool(int(g[f"{tag}_inc"]))
+        out = oenc.embedder_embed(g[x], n, g[x].shape[-1], max_freq_log2=mx_, include_input=inc)
+        assert out.shape[-1] == int(g[f"{tag}_dim"])
+        np.testing.assert_array_equal(out, g[f"{tag}_out"])
+
+
 def test_pe_sinusoidal(golden):
     g = golden("pe_sinusoidal")
     assert oenc.sinusoidal_out_dim(2, 10) == int(g["out_dim"]) == 40
