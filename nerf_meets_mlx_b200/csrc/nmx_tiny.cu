@@ -462,6 +462,7 @@ tiny_bwd_kernel(const TinyArgs a, const bf16* __restrict__ x0, int ldx0, const f
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) C[nt][0] = C[nt][1] = C[nt][2] = C[nt][3] = 0.0f;
       mma_layer<4, 8>(C, Y, wbh + (l - 1) * 2048, lane);
+      __syncwarp();  // stmatrix rows were written by other lanes of this warp
       load_frag(sm_fh + (l - 1) * kTile * 2, A);
       mask_pack(C, A, Y);
       store_frag(sm_fy + (l - 1) * kTile * 2, Y);
