@@ -585,11 +585,7 @@ int check_desc(const TinyMlpDesc& d) {
     set_error("tiny MLP: 1 <= D <= %d (D = 4: in_pos 32 only), in_pos in {32, 64}, 1 <= out_ch <= 8", kTinyMaxLayers);
     return NMX_E_BADARG;
   }
-  // vector atomics / loads need even parameter offsets (true for every packed layout of such a net)
-  if ((d.wo_off & 1) || (reinterpret_cast<uintptr_t>(d.params) & 15)) {
-    set_error("tiny MLP: parameter vector must be 16-byte aligned with even layer offsets");
-    return NMX_E_BADARG;
-  }
+  // the weight gradients are flushed as float2 atomics: even weight offsets (true for every packed layout of such a net)
   for (int l = 0; l < d.D; ++l)
     if (d.w_off[l] & 1) { set_error("tiny MLP: odd weight offset"); return NMX_E_BADARG; }
   return 0;
@@ -650,7 +646,7 @@ int launch_tiny_bwd(const TinyMlpDesc& d, const bf16* x0, int ldx0, const float*
   int rc = check_desc(d);
   if (rc) return rc;
   if (d.P == 0) return 0;
-  if ((ldx0 & 7) || (reinterpret_cast<uintptr_t>(x0) & 15) || (reinterpret_cast<uintptr_t>(d_params) & 15) ||
+  if ((ldx0 & 7) || (reinterpret_cast<uintptr_t>(x0) & 15) || (reinterpret_cast<uintptr_t>(d_params) & 7) ||
       (d_input && (reinterpret_cast<uintptr_t>(d_input) & 15))) {
     set_error("tiny MLP backward: operands must be 16-byte aligned");
     return NMX_E_BADARG;
