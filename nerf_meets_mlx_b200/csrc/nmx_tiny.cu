@@ -6,9 +6,10 @@
 //
 // Why a separate kernel: at width 64 the per-layer path is a dozen launches that each stream a [P, 64] tensor through HBM
 // (262 144 points: ~220 us of the 620 us C4 step).  The whole net is 24 KB of bf16 weights and 13 KFLOP per point, so
-// the op is bound by its own input / output bytes, not by the tensor pipe: the right tool is a register-resident chain of
-// warp-level mma.sync m16n8k16 tiles (a 128-row tcgen05 tile with its TMEM round trip per layer only adds latency at
-// K = N = 64).  One warp owns 16 points; the fp32 accumulator fragment of layer l IS the bf16 A fragment of layer l+1
+// the op is far from the tcgen05 roofline either way; this version is a register-resident chain of warp-level mma.sync
+// m16n8k16 tiles (no TMEM round trip per K = N = 64 layer).  Measured (profiles/r2_tiny_mlp_ncu.txt): forward 20 us,
+// backward 57 us per 262 144 points, HMMA pipe 40 / 46 % busy -- the warp-MMA path itself is the next bound, so the
+// follow-up is the same chain on tcgen05 tiles of 128 points.  One warp owns 16 points; the fp32 accumulator fragment of layer l IS the bf16 A fragment of layer l+1
 // after ReLU + packing, so activations never leave registers.
 //
 //   forward : x[P, in] fp32 -> out[P, out_ch] fp32; training additionally keeps the bf16 copy of x (64 B/point) -- the
